@@ -1,0 +1,951 @@
+"""CPU oracle: a NumPy restatement of the lmdec decomposition hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``lmdec_b200/`` may import this module; only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs do, and only as the
+checker / the reported CPU baseline -- never as the thing shipped.
+
+What it restates (reference = TNonet/lmdec, paths relative to the reference checkout):
+
+* the block power iteration driver                lmdec/decomp/iter_methods.py:133-218, 350-433, 458-480, 537-600
+* start matrices                                  lmdec/decomp/init_methods.py:13-40, 43-115, 118-151, 154-189
+* moments / mean-imputation / operator building   lmdec/decomp/utils.py:33-82, 120-192, 195-289
+* lazy sum / product operator algebra             lmdec/array/stacked.py:152-217, 247-265 ; lmdec/array/chained.py:159-252
+* iterate -> (U,S,V)                              lmdec/array/matrix_ops.py:19-99, 102-155, 158-198
+* convergence metrics                             lmdec/array/metrics.py:37-105, 108-172, 175-235
+* u/s formatting for rmse                         lmdec/array/transform.py:8-78
+* row sampling / partitions                       lmdec/array/random.py:6-64, 79-92, 188-278
+* legacy centred/scaled operator                  lmdec/array/scaled_legacy.py:11-165, 168-612
+
+Third-party arithmetic that is NOT in the reference tree and is restated from its published algorithm:
+
+* ``dask.array.linalg.tsqr`` (dask is unpinned in the reference: no setup.py / requirements): blockwise
+  Householder QR, QR of the stacked R factors, ``Q = Q1 Q2``; with ``compute_svd=True`` additionally
+  ``SVD(R) = U_R S Vh`` and returns ``(Q U_R, S, Vh)``.  Mathematically this is a thin QR followed by an SVD
+  of the small R; restated here as ``np.linalg.qr`` + ``np.linalg.svd``.  Column signs are LAPACK-dependent, so
+  parity is only ever asserted on sign/rotation-invariant quantities (S, ``subspace_dist``).
+* ``sparse.COO.dot``: restated with ``scipy.sparse``.
+* dask's per-chunk RNG (``rnormal_start``, the ``lmbd`` noise) is not reproducible outside dask: the oracle takes
+  the start matrix / the noise generator as explicit arguments (``x0=``, ``rng=``).
+
+Pinning: ``tests/test_oracle_golden.py`` checks this module against the reference's stored known-answer SVD
+(``lmdec/examples/ex1_{Uk,Sk,Vk}.npy``, committed under ``tests/golden/``) and against every analytic
+known-answer case in the reference's own tests for this path (tests/test_iter_methods.py, test_metrics.py,
+test_matrix_ops.py, test_random.py, test_decomp_utils.py, test_scaledcenterarray.py, test_init_methods.py).
+"""
+from __future__ import annotations
+
+import time
+import warnings
+from collections import namedtuple
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import scipy.sparse as sp
+
+PowerMethodSummary = namedtuple("PowerMethodSummary", ["time", "acc", "iter"])  # decomp/utils.py:12
+
+
+# --------------------------------------------------------------------------------------------------------------
+# tsqr  (dask.array.linalg.tsqr, called at iter_methods.py:382, init_methods.py:35,144, matrix_ops.py:72,94)
+# --------------------------------------------------------------------------------------------------------------
+def tsqr(x: np.ndarray, compute_svd: bool = False):
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim != 2:
+        raise ValueError("tsqr expects a 2-D array")
+    if not np.all(np.isfinite(x)):
+        # LAPACK (through dask/numpy) raises LinAlgError on NaN/Inf input: tests/test_iter_methods.py:318-325
+        raise np.linalg.LinAlgError("SVD did not converge (non-finite input)")
+    q, r = np.linalg.qr(x, mode="reduced")
+    if not compute_svd:
+        return q, r
+    u_r, s, vh = np.linalg.svd(r, full_matrices=False)
+    return q @ u_r, s, vh
+
+
+# --------------------------------------------------------------------------------------------------------------
+# partitions and sampling  (array/random.py)
+# --------------------------------------------------------------------------------------------------------------
+def _shape2(array_shape) -> Tuple[int, int]:  # random.py:67-76
+    if len(array_shape) == 2:
+        return int(array_shape[0]), int(array_shape[1])
+    if len(array_shape) == 1:
+        return int(array_shape[0]), 1
+    raise ValueError("Can only split 2-D arrays. Shape = {}".format(array_shape))
+
+
+def array_split(array_shape, f: float, axis: int = 0, seed: int = 42):  # random.py:37-64
+    n, p = _shape2(array_shape)
+    if axis == 1:
+        return array_split((p, n), f=f, axis=0, seed=seed)
+    if axis != 0:
+        raise ValueError("Can only split on axis = 0 or 1. axis = {}".format(axis))
+    sample_size = int(f * n)
+    if f > 1:
+        raise ValueError("Cannot split more than unity. p = {}".format(f))
+    if f < 0:
+        raise ValueError("Cannot split non-positive fraction. p = {}".format(f))
+    if sample_size == n:
+        warnings.warn("Degenerate Split. Decrease p. p = {} ~= 1".format(f))
+    elif sample_size == 0:
+        warnings.warn("Degenerate Split. Decrease p. p = {} ~= 0".format(f))
+    index = np.arange(0, n)
+    np.random.seed(seed=seed)  # legacy global RandomState: the reference does exactly this
+    np.random.shuffle(index)
+    return np.sort(index[:sample_size]), np.sort(index[sample_size:])
+
+
+def array_constant_partition(array_shape, f: float, min_size: int = 5, axis: int = 0) -> List[slice]:  # :239-278
+    n, p = _shape2(array_shape)
+    if axis == 1:
+        return array_constant_partition((p, n), f=f, min_size=min_size, axis=0)
+    if axis != 0:
+        raise ValueError("Can only partition on axis = 0 or 1. axis = {}".format(axis))
+    if f <= 0:
+        raise ValueError("Cannot partition with non-positive fraction.")
+    if f > 0.5:
+        raise ValueError("Cannot partition with fraction more than 0.5.")
+    if min_size < 1:
+        raise ValueError("Min size must be a positive integer.")
+    num_partitions = int(1 / f)
+    if num_partitions == 1:
+        warnings.warn("Only 1 Partition was created. int(1/p) == 1")
+    size = max(n // num_partitions, min_size)
+    out, start, left = [], 0, n
+    while left >= size:
+        out.append(slice(start, start + size))
+        start += size
+        left -= size
+    if left > 0 and left >= min_size:
+        out.append(slice(start, n))
+    elif min_size > left > 0:
+        out[-1] = slice(out[-1].start, n)
+    return out
+
+
+def cumulative_partition(parts: Sequence[slice]) -> List[slice]:  # random.py:79-92
+    out = []
+    start, step, prev_end = parts[0].start, parts[0].step, parts[0].start
+    for part in parts:
+        if part.step != step:
+            raise ValueError("Cannot find cumulative partition of non uniform step slices.")
+        if prev_end == part.start:
+            out.append(slice(start, part.stop, step))
+            prev_end = part.stop
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# small matrix helpers  (array/matrix_ops.py, array/transform.py)
+# --------------------------------------------------------------------------------------------------------------
+def diag_dot(diag_array, x):  # matrix_ops.py:174-198
+    diag_array = np.asarray(diag_array)
+    x = np.asarray(x)
+    if x.ndim not in (1, 2):
+        raise ValueError("x must have (M, K) or (K, ). Current Shape = {}".format(x.shape))
+    if diag_array.shape[0] != x.shape[0]:
+        raise ValueError("shapes {} and {} not aligned".format(diag_array.shape, x.shape))
+    if diag_array.ndim not in (1, 2):
+        raise ValueError("diag_array must have dimension (K, ) or (K, 1)")
+    d = np.squeeze(diag_array) if diag_array.ndim == 2 else diag_array
+    d = np.atleast_1d(d)
+    return d * x if x.ndim == 1 else d[:, None] * x
+
+
+def svd_to_trunc_svd(u=None, s=None, v=None, k=None):  # matrix_ops.py:140-155
+    out = []
+    if u is not None:
+        out.append(u[:, :k])
+    if s is not None:
+        out.append(s[:k])
+    if v is not None:
+        out.append(v[:k, :])
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+def subspace_to_V(x, a, k=None):  # matrix_ops.py:89-99
+    x_t = a.T.dot(x)
+    v, _, _ = tsqr(np.asarray(x_t), compute_svd=True)
+    v = v.T
+    if k:
+        v = svd_to_trunc_svd(v=v, k=k)
+    return v
+
+
+def subspace_to_SVD(x, a=None, k=None, full_v=False, sqrt_s=True):  # matrix_ops.py:71-86
+    x = np.asarray(x)
+    if x.ndim == 1:
+        x = x[:, None]
+    u, s, v = tsqr(x, compute_svd=True)
+    if full_v:
+        v = subspace_to_V(x, a, k)
+    if sqrt_s:
+        s = np.sqrt(s)
+    if k:
+        u, s, v = svd_to_trunc_svd(u, s, v, k=k)
+    return u, s, v
+
+
+def acc_format_svd(u, s, array_shape, square=True):  # transform.py:30-78
+    m, n = array_shape
+    u = np.asarray(u)
+    if u.ndim == 1:
+        m_vector, k_vector = u.shape[0], 1
+    elif u.ndim == 2:
+        m_vector, k_vector = u.shape
+    else:
+        raise Exception("u is of the wrong shape, {}".format(u.shape))
+    s_copy = np.array(s, dtype=np.float64, copy=True)
+    if square:
+        s_copy = np.square(s_copy)
+    if s_copy.ndim == 1:
+        k_values = s_copy.shape[0]
+        s_copy = np.diag(s_copy)
+    elif s_copy.ndim == 2:
+        if s_copy.shape[0] != s_copy.shape[1]:
+            raise Exception("s is the wrong shape, {}".format(s_copy.shape))
+        k_values = s_copy.shape[0]
+        s_copy = np.diag(np.diag(s_copy))
+    else:
+        raise Exception("s is the wrong shape, {}".format(s_copy.shape))
+    if m == m_vector:
+        pass
+    elif m == k_vector:
+        u = u.T
+        m_vector, k_vector = k_vector, m_vector
+    else:
+        raise Exception("u or s is of the wrong shape")
+    if k_values != k_vector:
+        raise Exception("u or s is of the wrong shape")
+    return u, s_copy
+
+
+# --------------------------------------------------------------------------------------------------------------
+# metrics  (array/metrics.py)
+# --------------------------------------------------------------------------------------------------------------
+def q_value_converge(si, sj, scale=True, norm=2):  # metrics.py:219-235
+    si, sj = np.asarray(si, dtype=np.float64), np.asarray(sj, dtype=np.float64)
+    if si.shape != sj.shape:
+        raise ValueError("Shapes of si and sj must match. Current {} != {}".format(si.shape, sj.shape))
+    acc = np.linalg.norm(si - sj, norm)
+    if scale:
+        acc /= (np.linalg.norm(si, norm) + np.linalg.norm(sj, norm)) / 2
+    return float(acc)
+
+
+def subspace_dist(vi, vj, s, power=2, epsilon=1e-6):  # metrics.py:70-105
+    vi, vj, s = np.asarray(vi), np.asarray(vj), np.asarray(s, dtype=np.float64)
+    if vi.shape[0] == len(s):
+        vi = vi.T
+    if vj.shape[0] == len(s):
+        vj = vj.T
+    if vi.shape[0] != vj.shape[0]:
+        raise ValueError("Shape Error between vi, {},  and vj, {}".format(vi.shape, vj.shape))
+    l = np.linalg.svd(vi.T.dot(vj), compute_uv=False)
+    if max(l) > 1 + 1e-6 or min(l) < -1e-6:
+        raise ValueError("Norm of vi or vj was not 1.")
+    if power in (float("inf"), -1):
+        idx = np.argmin(s) if power == -1 else np.argmax(s)
+        val = s[idx]
+        s = np.zeros_like(s)
+        s[idx] = val
+        power = 1
+    weighted = np.squeeze((s ** power).dot(l))
+    return float(1 - weighted / (np.sum(s ** power) + epsilon))
+
+
+def rmse_k(array, u, s, format_us=True, factor=None):  # metrics.py:151-172
+    n, p = array.shape
+    u = np.asarray(u)
+    k = u.shape[1]
+    if format_us:
+        u, s = acc_format_svd(u, s, array.shape, square=False)
+    aatx = np.asarray(array.dot(np.asarray(array.T.dot(u))))
+    if factor is not None:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            aatx = aatx / factor  # factor=False (from factor=None upstream) -> inf: reference quirk kept
+    acc = np.linalg.norm(aatx - u.dot(s), ord="fro")
+    return float(acc / np.sqrt(n * k * p))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# lazy operator algebra  (array/stacked.py, array/chained.py)
+# --------------------------------------------------------------------------------------------------------------
+class _Dense:
+    """ndarray / scipy-sparse leaf with the operator protocol (.shape .ndim .T .dot [rows])."""
+
+    def __init__(self, a):
+        self.a = a
+
+    @property
+    def shape(self):
+        return self.a.shape
+
+    @property
+    def ndim(self):
+        return len(self.a.shape)
+
+    @property
+    def T(self):
+        return _Dense(self.a.T)
+
+    def dot(self, x):
+        return np.asarray(self.a.dot(np.asarray(x, dtype=np.float64)))
+
+    def reshape(self, *shape):
+        if sp.issparse(self.a):
+            return _Dense(self.a.reshape(*shape))
+        return _Dense(np.reshape(self.a, shape))
+
+    def __getitem__(self, item):
+        a = self.a
+        if sp.issparse(a):
+            a = a.tocsr()
+        return _Dense(a[item])
+
+    def toarray(self):
+        return np.asarray(self.a.todense()) if sp.issparse(self.a) else np.asarray(self.a)
+
+
+def _leaf(a):
+    return a if isinstance(a, (_Dense, StackedArray, ChainedArray)) else _Dense(a)
+
+
+class StackedArray:
+    """A = B + C + ...  (array/stacked.py:13-284)."""
+
+    def __init__(self, arrays):
+        self.arrays = [_leaf(a) for a in arrays]
+        self.shape = tuple(np.broadcast_shapes(*[a.shape for a in self.arrays]))
+        self.ndim = len(self.shape)
+
+    @property
+    def T(self):  # stacked.py:152-166
+        if self.ndim != 2:
+            raise NotImplementedError
+        n, p = self.shape
+        out = []
+        for a in self.arrays:
+            if a.shape == (n, p):
+                out.append(a.T)
+            elif a.shape in [(p,), (1, p)]:
+                out.append(a.reshape(p, 1))
+            else:
+                out.append(a.reshape(1, n))
+        return StackedArray(out)
+
+    def dot(self, x):  # stacked.py:196-217
+        x = np.asarray(x, dtype=np.float64)
+        if self.ndim != 2 or x.ndim > 2:
+            raise NotImplementedError
+        n, p = self.shape
+        total = None
+        for a in self.arrays:
+            if a.shape == self.shape:
+                out = a.dot(x)
+            elif a.shape == (n, 1):
+                out = a.toarray() * x.sum(axis=0)
+                if x.ndim == 1:
+                    out = np.squeeze(out)
+            elif a.shape == (1, p):
+                out = np.squeeze(a.toarray()).dot(x)
+            elif a.shape == (p,):
+                out = a.toarray().dot(x)
+            else:
+                raise NotImplementedError
+            total = out if total is None else total + out
+        return total
+
+    def __getitem__(self, item):  # stacked.py:247-265
+        if not isinstance(item, tuple):
+            return StackedArray([a[item] for a in self.arrays])
+        if len(item) > self.ndim:
+            raise IndexError("Too many indices for array")
+        subs = []
+        for a in self.arrays:
+            sub_item = []
+            for i, s in zip(item[-len(a.shape):], a.shape):
+                if s > 1:
+                    sub_item.append(i)
+                elif isinstance(i, slice):
+                    sub_item.append(slice(None, None, None))
+                else:
+                    sub_item.append(0)
+            subs.append(a[tuple(sub_item)])
+        return StackedArray(subs)
+
+    def toarray(self):
+        total = None
+        for a in self.arrays:
+            d = a.toarray()
+            total = d if total is None else total + d
+        return total
+
+    __array__ = lambda self, dtype=None, copy=None: self.toarray()
+
+
+class ChainedArray:
+    """A = B @ C @ ... with 1-D members read as diagonals  (array/chained.py:12-269)."""
+
+    def __init__(self, arrays):
+        self.arrays = [_leaf(a) for a in arrays]
+        prev = None
+        for a in self.arrays:
+            if a.ndim > 2:
+                raise NotImplementedError("expected 1D or 2D arrays")
+            n, p = (a.shape[0], a.shape[0]) if a.ndim == 1 else a.shape
+            if prev is not None and prev != n:
+                raise ValueError("expected chain-able dimensions, got {}".format([b.shape for b in self.arrays]))
+            prev = p
+        first, last = self.arrays[0], self.arrays[-1]
+        self.shape = (first.shape[0], last.shape[0] if last.ndim == 1 else last.shape[1])
+        self.ndim = 2
+
+    @property
+    def T(self):  # chained.py:159-163
+        return ChainedArray(list(reversed([a.T if a.ndim == 2 else a for a in self.arrays])))
+
+    def dot(self, x):  # chained.py:169-177
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim > 2:
+            raise NotImplementedError
+        for a in reversed(self.arrays):
+            x = a.dot(x) if a.ndim == 2 else diag_dot(a.toarray(), x)
+        return x
+
+    def __getitem__(self, item):  # chained.py:182-252 (slices only; fancy rows -> NotImplementedError)
+        if not isinstance(item, tuple):
+            item = (item,)
+        if len(item) > 2:
+            raise IndexError("Too many indices for array")
+        if any(not isinstance(i, slice) for i in item):
+            raise NotImplementedError("Only implements slice indexing")
+        arrays = list(self.arrays)
+        if arrays[0].ndim == 1:
+            if item[0] != slice(None, None, None):
+                raise NotImplementedError("row-slicing a leading diagonal is out of scope for the oracle")
+        else:
+            arrays[0] = arrays[0][item[0], :]
+        if len(item) == 2 and item[1] != slice(None, None, None):
+            if arrays[-1].ndim == 1:
+                raise NotImplementedError("column-slicing a trailing diagonal is out of scope for the oracle")
+            arrays[-1] = arrays[-1][:, item[1]]
+        return ChainedArray(arrays)
+
+    def toarray(self):
+        out = None
+        for a in self.arrays:
+            d = a.toarray()
+            d = np.diag(d) if d.ndim == 1 else d
+            out = d if out is None else out @ d
+        return out
+
+    __array__ = lambda self, dtype=None, copy=None: self.toarray()
+
+
+def as_operator(a):
+    """``da.array(data)`` at iter_methods.py:357 -- keep Stacked/Chained, wrap anything else."""
+    if isinstance(a, (StackedArray, ChainedArray, ScaledCenterArray, _Dense)):
+        return a
+    a = np.asarray(a)
+    return _Dense(a)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# moments, mean imputation, make_snp_array  (decomp/utils.py)
+# --------------------------------------------------------------------------------------------------------------
+def get_array_moments(array, mean=True, std=True, std_method="binom", axis=0):  # utils.py:64-82
+    array = np.asarray(array, dtype=np.float64)
+    array_mean = array_std = None
+    if mean:
+        array_mean = np.nanmean(array, axis=axis)
+    if std:
+        if std_method == "binom":
+            u = (array_mean if mean else np.nanmean(array, axis=axis)) / 2
+            array_std = np.sqrt(2 * u * (1 - u))
+        elif std_method == "norm":
+            array_std = np.nanstd(array, axis=axis)
+        else:
+            raise NotImplementedError(f"std_method, {std_method}, is not implemented ")
+    return array_mean, array_std
+
+
+def mask_imputation(array, mask_values=None, fill_value=0, mask_method="mean", mask_axis=0):  # utils.py:164-192
+    array = np.asarray(array, dtype=np.float64)
+    if mask_values is None:
+        if mask_method != "mean":
+            raise NotImplementedError(f"mask_method, {mask_method}, is not implemented ")
+        mask_values = np.nanmean(array, axis=mask_axis)
+    coords = np.where(np.isnan(array))
+    if not len(coords[0]):
+        raise ValueError("expected array to have maskable values, but got none.")
+    data = np.asarray(mask_values)[coords[1 - mask_axis]]
+    mask = sp.coo_matrix((data, coords), shape=array.shape).tocsr()
+    filled = np.where(np.isnan(array), float(fill_value), array)
+    return filled, mask
+
+
+def make_snp_array(array, mean=True, std=True, std_method="binom", dtype="int8", mask_method="mean", mask_nan=True):
+    """utils.py:259-289:  SNP = ((filled + mask) - mean) * diag(1/std), built lazily."""
+    array = np.asarray(array, dtype=np.float64)
+    mean_array, std_array = get_array_moments(array, mean=mean, std=std, std_method=std_method, axis=0)
+    mask_valid = False
+    mask_array = None
+    if mask_nan:
+        try:
+            if mask_method == "mean" and mean:
+                array, mask_array = mask_imputation(array, mean_array, fill_value=0, mask_axis=0)
+            else:
+                array, mask_array = mask_imputation(array, mask_method=mask_method, fill_value=0, mask_axis=0)
+            mask_valid = True
+        except ValueError:
+            pass
+    with np.errstate(invalid="ignore"):
+        out = array.astype(dtype)
+    if mask_nan and mask_valid:
+        out = StackedArray((out, mask_array))
+    if mean:
+        out = StackedArray((out, -mean_array))
+    if std:
+        with np.errstate(divide="ignore"):
+            out = ChainedArray((out, 1 / std_array))
+    return out if not isinstance(out, np.ndarray) else _Dense(out)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# start matrices  (decomp/init_methods.py)
+# --------------------------------------------------------------------------------------------------------------
+def rnormal_start(array, k, seed=42):
+    """init_methods.py:180-184 draws from dask's chunked RandomState(seed); that stream depends on the dask
+    chunking and cannot be reproduced here -> plain NumPy stream with the same seed (documented divergence;
+    parity runs inject ``x0`` instead)."""
+    n = array.shape[0]
+    return np.random.RandomState(seed).standard_normal(size=(n, k))
+
+
+def v_init(array, v):  # init_methods.py:33-35
+    u, _, _ = tsqr(np.asarray(array.dot(v)), compute_svd=True)
+    return u
+
+
+def sub_svd_init(array, k, warm_start_row_factor=5, seed=42):  # init_methods.py:90-115, 144-147
+    rows = warm_start_row_factor * k
+    n, p = array.shape
+    idx, _ = array_split(array.shape, f=rows / n, axis=0, seed=seed)
+    try:
+        sub = array[idx, :]
+    except NotImplementedError:
+        sub = array[0:rows, :]
+    sub_t = np.asarray(sub.toarray() if hasattr(sub, "toarray") else sub).T
+    v, _, _ = tsqr(sub_t, compute_svd=True)
+    return v_init(array, v[:, :k])
+
+
+# --------------------------------------------------------------------------------------------------------------
+# drivers  (decomp/iter_methods.py)
+# --------------------------------------------------------------------------------------------------------------
+class _IterAlgo:
+    def __init__(self, max_iter=None, scoring_method=None, tol=None, factor=None, time_limit=None, warn=None):
+        if max_iter is None:
+            self.max_iter = 50
+        else:
+            if max_iter <= 0:
+                raise ValueError("max_iter must be a postitive integer")
+            if int(max_iter) != max_iter:
+                raise ValueError("max_iter must be a integer")
+            self.max_iter = max_iter
+        if scoring_method is None:
+            scoring_method = "q-vals"
+        if time_limit is None:
+            self.time_limit = 1000
+        else:
+            if time_limit <= 0:
+                raise ValueError("time_limit must be a positive amount")
+            self.time_limit = time_limit
+        if tol is None:
+            tol = 0.1e-3
+        if not isinstance(tol, list):
+            tol = [tol]
+        if not isinstance(scoring_method, list):
+            scoring_method = [scoring_method]
+        if len(scoring_method) != len(tol):
+            raise ValueError("tolerance, tol, specification must match with convergence criteria")
+        if any(x not in ["q-vals", "rmse", "v-subspace"] for x in scoring_method):
+            raise ValueError("Must use scoring method in {}".format(["q-vals", "rmse", "v-subspace"]))
+        self.factor = factor
+        self.warn = bool(warn)
+        self.tol = tol
+        self.scoring_method = scoring_method
+        self.history = None
+        self.num_iter = None
+        self.array = None
+
+    def _reset_history(self):
+        self.history = PowerMethodSummary(
+            time={"start": None, "stop": None, "iter": [], "step": [], "acc": []},
+            acc={"q-vals": [], "rmse": [], "v-subspace": []},
+            iter={"U": [], "S": [], "V": [], "last_value": []},
+        )
+
+    @property
+    def time(self):
+        return self.history.time["stop"] - self.history.time["start"]
+
+    def svd(self, array, verbose=False, return_history=False, **kwargs):  # iter_methods.py:175-218
+        try:
+            return self._svd(array, return_history=return_history, **kwargs)
+        except KeyboardInterrupt:  # wrappers/recover_iter.py:9-18
+            if self.history.iter["last_value"]:
+                return self.history.iter["last_value"]
+            raise
+
+    def _svd(self, array, return_history=False, **kwargs):
+        self._reset_history()
+        self.history.time["start"] = time.time()
+        x_k = self._initialization(array, **kwargs)
+        converged = False
+        for i in range(1, self.max_iter + 1):
+            self.num_iter = i
+            t0 = time.time()
+            acc_list = self._solution_accuracy(x_k)
+            self.history.time["acc"].append(time.time() - t0)
+            for method, acc, tol in zip(self.scoring_method, acc_list, self.tol):
+                self.history.acc[method].append(acc)
+                if acc <= tol:
+                    converged = True
+            if converged:
+                break
+            t1 = time.time()
+            x_k = self._solution_step(x_k)
+            self.history.time["step"].append(time.time() - t1)
+            self.history.time["iter"].append(time.time() - t0)
+            if time.time() - self.history.time["start"] > self.time_limit:
+                break
+        result = self._finalization(x_k, return_history=return_history)
+        self.history.time["stop"] = time.time()
+        if self.warn and not converged:
+            warnings.warn("Did not converge.")
+        return result
+
+
+class PowerMethod(_IterAlgo):
+    def __init__(self, k=10, max_iter=50, scoring_method="q-vals", tol=0.1, factor="n", lmbd=0.01, buffer=10,
+                 sub_svd_start=True, init_row_sampling_factor=5, time_limit=1000, warn=False):
+        super().__init__(max_iter=max_iter, scoring_method=scoring_method, tol=tol, factor=factor,
+                         time_limit=time_limit, warn=warn)
+        if int(k) <= 0:
+            raise ValueError("k must be a positive integer")
+        if int(buffer) < 0:
+            raise ValueError("buffer must be a non-negative integer")
+        self.k, self.buffer, self.lmbd = int(k), int(buffer), lmbd
+        self.sub_svd_start = sub_svd_start
+        if init_row_sampling_factor <= 0:
+            raise ValueError("init_row_sampling_factor must be a positive value")
+        self.init_row_sampling_factor = init_row_sampling_factor
+
+    def _resolve_factor(self):  # iter_methods.py:359-364 (mutates self.factor, as the reference does)
+        if self.factor == "n":
+            self.factor = self.array.shape[0]
+        elif self.factor == "p":
+            self.factor = self.array.shape[1]
+        elif self.factor is None:
+            self.factor = False
+
+    def _initialization(self, data, x0=None, rng=None, **kwargs):  # iter_methods.py:350-379
+        vec_t = self.k + self.buffer
+        if len(data.shape) != 2:
+            raise ValueError("expected a 2-D array")
+        if vec_t > min(data.shape):
+            raise ValueError("Cannot find more than min(n,p) singular values of array function.")
+        self.array = as_operator(data)
+        self._resolve_factor()
+        if x0 is not None:
+            return np.array(x0, dtype=np.float64, copy=True)
+        if self.sub_svd_start:
+            x = sub_svd_init(self.array, k=vec_t, warm_start_row_factor=self.init_row_sampling_factor)
+            if self.lmbd:
+                rng = rng if rng is not None else np.random.default_rng()
+                c_norms = np.linalg.norm(x, 2, axis=0)
+                x = x * (1 - self.lmbd)
+                x = x + (self.lmbd * c_norms / np.sqrt(x.shape[0])) * rng.standard_normal(size=x.shape)
+            return x
+        return rnormal_start(self.array, vec_t)
+
+    def _solution_step(self, x):  # iter_methods.py:381-386
+        q, _ = tsqr(x)
+        x = np.asarray(self.array.dot(np.asarray(self.array.T.dot(q))))
+        if self.factor:
+            x = x / self.factor
+        return x
+
+    def _solution_accuracy(self, x):  # iter_methods.py:391-419
+        full_v = any(m in self.scoring_method for m in ["rmse", "v-subspace"])
+        U_k, S_k, V_k = subspace_to_SVD(x, self.array, sqrt_s=True, k=self.k, full_v=full_v)
+        self.history.iter["last_value"] = (U_k, S_k, V_k)
+        acc_list = []
+        for method in self.scoring_method:
+            if method == "q-vals":
+                try:
+                    acc = q_value_converge(S_k, self.history.iter["S"][-1])
+                except IndexError:
+                    acc = float("INF")
+                self.history.iter["S"].append(np.array(S_k))
+            elif method == "rmse":
+                acc = rmse_k(self.array, U_k, S_k ** 2, factor=self.factor)
+            else:
+                try:
+                    acc = subspace_dist(V_k.T, self.history.iter["V"][-1].T, S_k)
+                except IndexError:
+                    acc = float("INF")
+                self.history.iter["V"].append(np.array(V_k))
+            acc_list.append(acc)
+        return acc_list
+
+    def _finalization(self, x, return_history):  # iter_methods.py:421-433
+        if self.history.iter["last_value"][2].shape[1] != self.array.shape[1]:
+            U, S, _ = self.history.iter["last_value"]
+            V = subspace_to_V(x, self.array, self.k)
+            self.history.iter["last_value"] = (U, S, V)
+        return self.history if return_history else self.history.iter["last_value"]
+
+
+class _vPowerMethod(PowerMethod):  # iter_methods.py:436-480
+    def __init__(self, v_start, k=None, buffer=None, max_iter=None, scoring_method=None, tol=None, full_svd=False,
+                 factor=None, warn=False):
+        _IterAlgo.__init__(self, max_iter=max_iter, scoring_method=scoring_method, tol=tol, factor=factor, warn=warn)
+        self.lmbd = 1
+        self.v_start, self.k, self.buffer, self.full_svd = np.asarray(v_start), k, buffer, full_svd
+
+    def _initialization(self, data, **kwargs):
+        self.array = data
+        return np.asarray(self.array.dot(self.v_start))
+
+    def _finalization(self, x, return_history):
+        if not self.full_svd:
+            return np.asarray(self.array.T.dot(x))
+        return PowerMethod._finalization(self, x, return_history=False)
+
+
+class SuccessiveBatchedPowerMethod(PowerMethod):  # iter_methods.py:483-600
+    def __init__(self, k=10, max_sub_iter=50, factor="n", scoring_method="q-vals", f=0.1, lmbd=0.1, tol=0.1,
+                 buffer=10, sub_svd_start=True, init_row_sampling_factor=5, max_sub_time=1000, warn=False):
+        super().__init__(k=k, max_iter=max_sub_iter, factor=factor, scoring_method=scoring_method, tol=tol,
+                         buffer=buffer, sub_svd_start=sub_svd_start,
+                         init_row_sampling_factor=init_row_sampling_factor, time_limit=max_sub_time, warn=warn)
+        self.f, self.lmbd, self.sub_svds = f, lmbd, None
+
+    def _reset_history(self):
+        super()._reset_history()
+        self.history.acc["sub_svd_acc"] = []
+        self.history.iter["sub_svd"] = []
+
+    def _svd(self, array, return_history=False, x0=None, rng=None, **kwargs):
+        self._reset_history()
+        self.history.time["start"] = time.time()
+        self.array = as_operator(array)
+        self._resolve_factor()
+        vec_t = self.k + self.buffer
+        partitions = cumulative_partition(array_constant_partition(self.array.shape, f=self.f, min_size=vec_t))
+        sub_array = self.array[partitions[0], :]
+        if x0 is not None:
+            x = np.array(x0, dtype=np.float64, copy=True)
+        elif self.sub_svd_start == "warm":
+            x = sub_svd_init(sub_array, k=vec_t, warm_start_row_factor=self.init_row_sampling_factor)
+        else:
+            x = rnormal_start(sub_array, k=vec_t)
+        x = np.asarray(sub_array.T.dot(x))
+        for part in partitions[:-1]:
+            pm = _vPowerMethod(v_start=x, k=self.k, buffer=self.buffer, max_iter=self.max_iter, factor=self.factor,
+                               scoring_method=self.scoring_method, tol=self.tol, warn=self.warn)
+            x = pm.svd(self.array[part, :])
+            self.history.iter["last_value"] = pm.history.iter["last_value"]
+            self.history.iter["sub_svd"].append(self.history.iter["last_value"])
+            if self.lmbd:
+                rng = rng if rng is not None else np.random.default_rng()
+                c_norms = np.linalg.norm(x, 2, axis=0)
+                x = x * (1 - self.lmbd)
+                x = x + (self.lmbd * c_norms / np.sqrt(x.shape[0])) * rng.standard_normal(size=x.shape)
+            if "v-subspace" in self.scoring_method:
+                self.history.iter["V"].append(pm.history.iter["V"][-1])
+            self.history.iter["S"].append(pm.history.iter["S"][-1])
+            self.history.acc["sub_svd_acc"].append(pm.history.acc)
+            self.history.time["iter"].append(pm.history.time)
+        pm = _vPowerMethod(v_start=x, k=self.k, buffer=self.buffer, max_iter=self.max_iter, factor=self.factor,
+                           scoring_method=self.scoring_method, tol=self.tol, full_svd=True, warn=self.warn)
+        pm.svd(self.array)
+        self.history.iter["last_value"] = pm.history.iter["last_value"]
+        self.history.iter["sub_svd"].append(self.history.iter["last_value"])
+        self.history.time["stop"] = time.time()
+        return self.history if return_history else self.history.iter["last_value"]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# legacy ScaledCenterArray  (array/scaled_legacy.py)
+# --------------------------------------------------------------------------------------------------------------
+class ArrayMoment:  # scaled_legacy.py:11-165
+    def __init__(self, a, std_dist="normal", warn=True):
+        if std_dist not in ["binom", "normal"]:
+            raise ValueError("std_dist must be either `binom` or `normal`")
+        self._array, self._std_dist, self._warn, self._std_tol = a, std_dist, warn, 1e-6
+        self.center_vector = self.scale_vector = self.sym_scale_vector = None
+
+    def _std_inverter(self, std):  # :60-85
+        std = np.array(std, dtype=np.float64, copy=True)
+        bad = np.where(std <= self._std_tol)[0]
+        if len(bad) > 0:
+            if self._warn:
+                warnings.warn("SNP Columns {} have low standard deviation. Setting STD of columns to 1".format(bad))
+            std[bad] = 1
+        return 1 / std
+
+    def fit(self):  # :87-99  (plain mean/std: NOT nan-aware)
+        a = np.asarray(self._array, dtype=np.float64)
+        self.center_vector = a.mean(axis=0)
+        if self._std_dist == "normal":
+            self.scale_vector = self._std_inverter(a.std(axis=0))
+        else:
+            p = self.center_vector / 2
+            self.scale_vector = self._std_inverter(np.sqrt(2 * p * (1 - p)))
+        self.sym_scale_vector = self.scale_vector ** 2
+
+
+def _squeeze_k1(f):  # matrix_ops.py:201-217
+    def wrapped(self, x):
+        x = np.asarray(x)
+        reshape = x.ndim == 2 and x.shape[1] == 1
+        if reshape:
+            x = np.squeeze(x, axis=1) if x.shape[0] != 1 else np.squeeze(x)
+        r = f(self, x)
+        return r[:, np.newaxis] if reshape else r
+    return wrapped
+
+
+class ScaledCenterArray:  # scaled_legacy.py:168-612
+    def __init__(self, scale=True, center=True, factor=None, std_dist=None, warn=True):
+        self.scale, self.center = scale, center
+        if factor not in [None, "n", "p"]:
+            raise ValueError('factor, {}, must be in [None, "n", "p"]'.format(factor))
+        self.factor = factor
+        if std_dist not in [None, "normal", "binom"]:
+            raise ValueError("std_dist must be in [None, 'normal', 'binom']")
+        self._std_dist = std_dist or "normal"
+        self._warn = warn
+        self._array = self._array_moment = self._factor_value = self._t_cache = None
+        self._t_flag = False
+
+    @classmethod
+    def fromScaledArray(cls, array, scaled_array, factor=None):  # :211-249
+        array = np.asarray(array, dtype=np.float64)
+        if (scaled_array.scale and array.shape[1] != len(scaled_array.scale_vector)) or \
+                (scaled_array.center and array.shape[1] != len(scaled_array.center_vector)):
+            raise ValueError("expected array to have matching second dimension with array_moment shape")
+        sa = cls(scale=scaled_array.scale, center=scaled_array.center, factor=factor,
+                 std_dist=scaled_array._std_dist, warn=scaled_array._warn)
+        sa._array = array
+        sa._array_moment = ArrayMoment(array, std_dist=scaled_array._std_dist, warn=scaled_array._warn)
+        if sa.factor:
+            n, p = array.shape
+            sa._factor_value = n if sa.factor == "n" else p
+        sa._array_moment.center_vector = scaled_array.center_vector
+        sa._array_moment.scale_vector = scaled_array.scale_vector
+        sa._array_moment.sym_scale_vector = scaled_array.scale_vector ** 2
+        return sa
+
+    def fit(self, a, x=None):  # :251-287
+        if self._t_flag:
+            raise ValueError("Cannot fit on a Transposed Array. Use <instance>.T to recover base array")
+        a = np.asarray(a, dtype=np.float64)
+        if a.ndim != 2:
+            raise ValueError("Cannot fit non-2D array.")
+        self._array = a
+        self._array_moment = ArrayMoment(a, std_dist=self._std_dist, warn=self._warn)
+        self._array_moment.fit()
+        if self.factor:
+            n, p = a.shape
+            self._factor_value = n if self.factor == "n" else p
+
+    def fit_x(self, x):
+        if len(np.shape(x)) > 2:
+            raise ValueError("Cannot fit on a {}-d array.".format(len(np.shape(x))))
+
+    @property
+    def center_vector(self):
+        if self._array_moment is None:
+            raise AttributeError("ScaledCenterArray is not fit")
+        return self._array_moment.center_vector
+
+    @property
+    def scale_vector(self):
+        if self._array_moment is None:
+            raise AttributeError("ScaledCenterArray is not fit")
+        return self._array_moment.scale_vector
+
+    @property
+    def factor_value(self):
+        return self.factor if self._factor_value is None else self._factor_value
+
+    @property
+    def shape(self):
+        return tuple(reversed(self._array.shape)) if self._t_flag else self._array.shape
+
+    @property
+    def T(self):  # :401-406, 445-448
+        if self._t_cache is None:
+            t = ScaledCenterArray.__new__(ScaledCenterArray)
+            t.__dict__.update(self.__dict__)
+            t._t_flag = not self._t_flag
+            t._t_cache = self
+            self._t_cache = t
+        return self._t_cache
+
+    def _center_x(self, x, dx, transpose=False):  # :518-524
+        if transpose:
+            return x - np.squeeze(np.outer(self.center_vector, dx.sum(axis=0)))
+        return x - self.center_vector.dot(dx)
+
+    @_squeeze_k1
+    def sym_mat_mult(self, x):  # :379-399
+        if self._t_flag:
+            raise NotImplementedError("sym_mat_mult is only implemented for non-transposed arrays")
+        x = np.asarray(x, dtype=np.float64)
+        x_h = self._array.T.dot(x)
+        if self.center:
+            x_h = self._center_x(x_h, x, transpose=True)
+        if self.scale:
+            x_h = diag_dot(self._array_moment.sym_scale_vector, x_h)
+        y = self._array.dot(x_h)
+        if self.center:
+            y = self._center_x(y, x_h, transpose=False)
+        if self.factor:
+            y = y / self._factor_value
+        return y
+
+    @_squeeze_k1
+    def dot(self, x):  # :526-542
+        x = np.asarray(x, dtype=np.float64)
+        if not self._t_flag and self.scale:
+            x = diag_dot(self.scale_vector, x)
+        y = self._array.T.dot(x) if self._t_flag else self._array.dot(x)
+        if self.center:
+            y = self._center_x(y, x, transpose=self._t_flag)
+        if self._t_flag and self.scale:
+            y = diag_dot(self.scale_vector, y)
+        return y
+
+    @property
+    def array(self):  # :408-437
+        a = self._array
+        if self.center:
+            a = a - self.center_vector
+        if self.scale:
+            a = diag_dot(self.scale_vector, a.T).T
+        return a.T if self._t_flag else a
+
+    def __getitem__(self, item):  # :577-612  (refits the moments on the selection)
+        if isinstance(item, tuple) and len(item) > 2:
+            raise IndexError("too many indices for array")
+        new = ScaledCenterArray(scale=self.scale, center=self.center, factor=self.factor,
+                                std_dist=self._std_dist, warn=self._warn)
+        base = self._array.T if self._t_flag else self._array
+        sub = base[item]
+        new.fit(sub)
+        return new
