@@ -1,0 +1,120 @@
+/* lmdec_b200 -- C ABI of the B200-native decomposition hot path.
+ *
+ * The reference (TNonet/lmdec) is pure Python: it has no FFI of its own.  The boundary its hot path sits behind is
+ * the duck-typed operator protocol  .dot(x) / .T.dot(y)  that PowerMethod._solution_step calls
+ * (lmdec/decomp/iter_methods.py:381-386) on the operator make_snp_array builds (lmdec/decomp/utils.py:195-289).
+ * Every entry point below replaces one of those reference call sites; the citation names it.  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller (Python/PyTorch) owns all memory;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it;
+ *   - return value 0 = ok, nonzero = error; lmdec_last_error() returns a message for the calling thread;
+ *   - no global state: thread-compatible (one stream per caller).
+ *
+ * Genotype store ("tile store"): 2-bit dosage codes, 4 per byte, LSB first: 0,1,2 = dosage, 3 = missing (NaN).
+ * A PLINK .bed byte (00 hom-A1, 01 missing, 10 het, 11 hom-A2; pandas_plink reads these as 0,NaN,1,2) maps to a
+ * store byte with  c' = (c >> 1) + ((c & 1) ? ((c >> 1) ? 1 : 3) : 0)  per 2-bit field; see lmdec_recode_bed.
+ * A store holds a logical  M x Kd  matrix (M = output rows of a product, Kd = the contraction axis) as
+ *   tile(mp, kc) = 8192 bytes for rows [128*mp, +128) x contraction [256*kc, +256), tiles ordered mp-major;
+ *   inside a tile: byte (t, b) of row t's 64 packed bytes sits at  (b/16)*2048 + t*16 + b%16
+ * so that one warp reads 512 contiguous bytes per 16-byte piece.  Padding codes are 0.
+ * A genotype matrix is kept as TWO stores: sample-major (M = samples, feeds A.dot) and SNP-major (M = SNPs, the
+ * .bed orientation, feeds A.T.dot).
+ */
+#ifndef LMDEC_B200_H
+#define LMDEC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMDEC_TILE_ROWS 128
+#define LMDEC_TILE_KD 256
+#define LMDEC_TILE_BYTES 8192
+
+enum lmdec_dtype { LMDEC_I8 = 0, LMDEC_U8 = 1, LMDEC_F32 = 2, LMDEC_F64 = 3 };
+
+const char* lmdec_last_error(void);
+int lmdec_abi_version(void);
+
+/* bytes of a tile store holding a logical M x Kd matrix */
+int64_t lmdec_store_bytes(int64_t M, int64_t Kd);
+
+/* Pack a dense block into a tile store.  Replaces  fill_array + astype(int8)  and the NaN scan of mask_imputation
+ * (lmdec/decomp/utils.py:15-30, 167-192, 272).  Element (m, kd) of the block is  src[m*stride_m + kd*stride_kd]
+ * (element strides), m in [0,block_m), kd in [0,block_kd); it is stored at logical position (m0+m, kd0+kd) of a store
+ * of logical size M x Kd.  m0 must be a multiple of 128 and kd0 of 256.  Values 0,1,2 are kept; NaN (float types) and
+ * negative / 3 (integer types) become the missing code; anything else increments *bad_count (int32, device).  */
+int lmdec_pack_2bit(const void* src, int dtype, int64_t stride_m, int64_t stride_kd, int64_t block_m, int64_t block_kd,
+                    int64_t m0, int64_t kd0, uint8_t* store, int64_t M, int64_t Kd, int32_t* bad_count, void* stream);
+
+/* Inverse of the above for tests: dst[m*ld + kd] (int8) = 0,1,2 or -1 for missing. */
+int lmdec_unpack_2bit(const uint8_t* store, int64_t M, int64_t Kd, int8_t* dst, int64_t ld, void* stream);
+
+/* PLINK .bed bytes (variant-major, rows padded to whole bytes, no 3-byte magic) -> SNP-major tile store.
+ * Replaces pandas_plink.read_plink as called by load_plink_array (lmdec/array/io.py:16-73).  */
+int lmdec_recode_bed(const uint8_t* bed, int64_t n_variants, int64_t n_samples, uint8_t* store, void* stream);
+
+/* Transpose one tile store into the other orientation (M x Kd -> Kd x M), codes untouched. */
+int lmdec_store_transpose(const uint8_t* src, int64_t M, int64_t Kd, uint8_t* dst, void* stream);
+
+/* Per-row code counts of a store: counts[m*4 + c] (int64) = #{kd < kd_limit : code(m,kd) == c}.  With the SNP-major
+ * store this is the exact integer content of get_array_moments' nanmean / nanstd (lmdec/decomp/utils.py:64-82):
+ * mean_j = (c1 + 2 c2) / (n - c3).  */
+int lmdec_code_counts(const uint8_t* store, int64_t M, int64_t Kd, int64_t kd_limit, int64_t* counts, void* stream);
+
+/* Quantise a float64 operand  B[kd, k] * row1[kd] (* row2[kd])  into P signed-byte planes laid out as the tensor-core
+ * B image: image[kd/32][N*32] in the no-swizzle K-major core-matrix order, column n = plane*K + k,
+ * value = round(B * mult[k]) written as balanced base-256 digits.  rows >= kd_limit and columns >= P*K are zero.
+ * row1/row2 may be NULL.  image2 (optional) receives the planes of B*row1*row2 (the mean-imputation operand
+ * mu o D T  of StackedArray.dot's sparse-mask term, lmdec/array/stacked.py:204-217).  */
+int lmdec_quantize_planes(const double* B, int64_t ldb, int64_t Kd, int64_t kd_limit, int K, int P, int N,
+                          const double* mult, const double* row1, const double* row2, int8_t* image1, int8_t* image2,
+                          void* stream);
+int64_t lmdec_image_bytes(int64_t Kd, int N);
+
+/* column-wise max |B[kd,k]*row1[kd](*row2[kd])| over kd < kd_limit -> out[k] (and out2[k] with row2), float64 */
+int lmdec_colabsmax(const double* B, int64_t ldb, int64_t kd_limit, int K, const double* row1, const double* row2,
+                    double* out, double* out2, void* stream);
+
+/* The hot product:  out[m, k] = sum_kd  value(m,kd) * q1[kd,k]  (+ miss(m,kd) * q2[kd,k])   exactly, in int64,
+ * where value is the dosage (missing -> 0), miss the missing indicator and q the integer the planes encode.
+ * Replaces the chunked int8->f64 matmuls of StackedArray.dot / ChainedArray.dot (lmdec/array/stacked.py:172-217,
+ * lmdec/array/chained.py:169-177) under PowerMethod._solution_step (lmdec/decomp/iter_methods.py:381-386) and
+ * ScaledCenterArray.sym_mat_mult / dot (lmdec/array/scaled_legacy.py:379-399, 526-542).
+ *   store, M, Kd       the tile store (logical size);  m_limit <= M rows are produced, kd_limit <= Kd is contracted
+ *   has_missing        0: every code is 0..2 (one MMA per tile);  1: also run the indicator plane
+ *   mode               0: out0 = value.q1 + miss.q2 (q2 = image2, or image1 when image2 is NULL)
+ *                      1: out0 = value.q1 ; out1 = miss.q1      (needs has_missing)
+ *   splits             split-K factor; 0 = choose; >1 accumulates with int64 atomics (outputs are zeroed here)
+ * out0/out1: int64 [m_limit, K] row-major.  */
+int lmdec_geno_matmul(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit, int has_missing,
+                      int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N, int64_t* out0,
+                      int64_t* out1, int splits, void* stream);
+
+/* out[m,k] = (acc0[m,k] + rowa[m]*acc1[m,k]) * colscale[k] * rowscale[m] + rowshift[m]*colshift[k]
+ * (any of acc1/rowa, rowscale, rowshift/colshift may be NULL).  The diag / rank-1 terms of the operator algebra:
+ * diag_dot (lmdec/array/matrix_ops.py:158-198), the (p,) mean term of StackedArray.dot (stacked.py:207-215),
+ * ScaledCenterArray._center_x/_scale_x (scaled_legacy.py:452-524).  */
+int lmdec_finalize(const int64_t* acc0, const int64_t* acc1, int64_t M, int K, const double* colscale,
+                   const double* rowa, const double* rowscale, const double* rowshift, const double* colshift,
+                   double* out, int64_t ldo, void* stream);
+
+/* G[K,K] = X^T X and colsum[K] of a float64 X[m, K] (ld = ldx): the Gram matrix CholeskyQR2 factors in place of
+ * dask tsqr (lmdec/decomp/iter_methods.py:382, lmdec/array/matrix_ops.py:72).  Deterministic two-stage reduction;
+ * work must hold lmdec_gram_work_doubles(m, K) doubles.  Also serves subspace_dist's Vi^T Vj (metrics.py:81) via Y. */
+int64_t lmdec_gram_work_doubles(int64_t m, int K);
+int lmdec_gram(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t m, int K, double* G, double* colsum,
+               double* work, void* stream);
+
+/* q_value_converge (lmdec/array/metrics.py:219-235): out[0] = ||si-sj||_2 / ((||si||+||sj||)/2) (scale != 0). */
+int lmdec_qvals(const double* si, const double* sj, int k, int scale, double* out, void* stream);
+/* rmse_k's Frobenius part (metrics.py:161): out[0] = sum_{m,k} (A[m,k] - B[m,k]*s[k])^2  (deterministic). */
+int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, const double* s, int64_t m, int K,
+                 double* out, double* work, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

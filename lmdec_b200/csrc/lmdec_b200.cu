@@ -1,0 +1,603 @@
+// C-ABI implementation (include/lmdec_b200.h): tile-store kernels, operand quantisation, the tcgen05 product, and the
+// small fp64 reductions of the power iteration.  sm_100a only; there is no CPU path in this library.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include "../../include/lmdec_b200.h"
+#include "geno_mma.cuh"
+
+namespace {
+thread_local char g_err[512] = "";
+int fail(const char* fmt, const char* a = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return 1;
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+}  // namespace
+
+namespace lmdec {
+
+// ------------------------------------------------------------------------------------------------ tile store
+__host__ __device__ inline size_t tile_offset(int64_t mp, int64_t kc, int64_t n_kc) {
+  return ((size_t)mp * n_kc + kc) * 8192;
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t code_of(T v, int* bad) {
+  if (v == (T)0) return 0;
+  if (v == (T)1) return 1;
+  if (v == (T)2) return 2;
+  if (v != v) return 3;  // NaN
+  *bad = 1;
+  return 3;
+}
+template <>
+__device__ __forceinline__ uint32_t code_of<int8_t>(int8_t v, int* bad) {
+  if (v >= 0 && v <= 2) return (uint32_t)v;
+  if (v < 0 || v == 3) return 3;
+  *bad = 1;
+  return 3;
+}
+template <>
+__device__ __forceinline__ uint32_t code_of<uint8_t>(uint8_t v, int* bad) {
+  if (v <= 3) return v;
+  if (v == 255) return 3;
+  *bad = 1;
+  return 3;
+}
+
+// one thread = one 16-byte unit (64 codes) of the store
+template <typename T>
+__global__ void pack_kernel(const T* __restrict__ src, int64_t stride_m, int64_t stride_kd, int64_t block_m,
+                            int64_t block_kd, int64_t m0, int64_t kd0, uint8_t* __restrict__ store, int64_t n_kc,
+                            int64_t mp0, int64_t kc0, int64_t n_mp_blk, int64_t n_kc_blk, int32_t* bad_count) {
+  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_units = n_mp_blk * n_kc_blk * 512;
+  if (unit >= n_units) return;
+  const int t = (int)(unit & 127);
+  const int piece = (int)((unit >> 7) & 3);
+  const int64_t tile = unit >> 9;
+  const int64_t kc = kc0 + tile % n_kc_blk, mp = mp0 + tile / n_kc_blk;
+  const int64_t m = mp * 128 + t - m0;           // row inside the block
+  const int64_t kd = kc * 256 + piece * 64 - kd0;  // first contraction index inside the block
+  uint32_t w[4] = {0, 0, 0, 0};
+  int bad = 0;
+  if (m >= 0 && m < block_m) {
+    const T* row = src + m * stride_m;
+#pragma unroll 4
+    for (int e = 0; e < 64; ++e) {
+      const int64_t g = kd + e;
+      if (g >= 0 && g < block_kd) w[e >> 4] |= code_of<T>(row[g * stride_kd], &bad) << (2 * (e & 15));
+    }
+  }
+  uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(store + tile_offset(mp, kc, n_kc) + piece * 2048 + t * 16) = v;
+  if (bad) atomicAdd(bad_count, 1);
+}
+
+__global__ void unpack_kernel(const uint8_t* __restrict__ store, int64_t M, int64_t Kd, int64_t n_kc,
+                              int8_t* __restrict__ dst, int64_t ld, int64_t n_units) {
+  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (unit >= n_units) return;
+  const int t = (int)(unit & 127);
+  const int piece = (int)((unit >> 7) & 3);
+  const int64_t tile = unit >> 9;
+  const int64_t kc = tile % n_kc, mp = tile / n_kc;
+  const int64_t m = mp * 128 + t;
+  if (m >= M) return;
+  const uint4 v = *reinterpret_cast<const uint4*>(store + tile_offset(mp, kc, n_kc) + piece * 2048 + t * 16);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  for (int e = 0; e < 64; ++e) {
+    const int64_t g = kc * 256 + piece * 64 + e;
+    if (g < Kd) {
+      const uint32_t c = (w[e >> 4] >> (2 * (e & 15))) & 3u;
+      dst[m * ld + g] = c == 3 ? (int8_t)-1 : (int8_t)c;
+    }
+  }
+}
+
+// counts per store row; one thread per row, coalesced 16-byte units across the warp
+__global__ void code_counts_kernel(const uint8_t* __restrict__ store, int64_t M, int64_t n_kc, int64_t kd_limit,
+                                   long long* __restrict__ counts) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int64_t mp = m >> 7;
+  const int t = (int)(m & 127);
+  const int64_t full_units = kd_limit / 64;  // 16-byte units entirely below the limit
+  long long c1 = 0, c2 = 0, c3 = 0;
+  for (int64_t u = 0; u * 64 < kd_limit; ++u) {
+    const int64_t kc = u >> 2;
+    const int piece = (int)(u & 3);
+    uint4 v = *reinterpret_cast<const uint4*>(store + tile_offset(mp, kc, n_kc) + piece * 2048 + t * 16);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (u >= full_units) {  // ragged tail: mask codes at or above the limit
+      const int keep = (int)(kd_limit - u * 64);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = keep - 16 * i;
+        if (k <= 0)
+          w[i] = 0;
+        else if (k < 16)
+          w[i] &= (1u << (2 * k)) - 1u;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t lo = w[i] & 0x55555555u, hi = (w[i] >> 1) & 0x55555555u;
+      c3 += __popc(lo & hi);
+      c1 += __popc(lo & ~hi);
+      c2 += __popc(hi & ~lo);
+    }
+  }
+  counts[m * 4 + 0] = kd_limit - c1 - c2 - c3;
+  counts[m * 4 + 1] = c1;
+  counts[m * 4 + 2] = c2;
+  counts[m * 4 + 3] = c3;
+}
+
+// .bed (variant-major, PLINK codes) -> SNP-major tile store (M = variants, Kd = samples)
+__global__ void recode_bed_kernel(const uint8_t* __restrict__ bed, int64_t n_variants, int64_t n_samples,
+                                  int64_t bytes_per_variant, uint8_t* __restrict__ store, int64_t n_kc,
+                                  int64_t n_units) {
+  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (unit >= n_units) return;
+  const int t = (int)(unit & 127);
+  const int piece = (int)((unit >> 7) & 3);
+  const int64_t tile = unit >> 9;
+  const int64_t kc = tile % n_kc, mp = tile / n_kc;
+  const int64_t j = mp * 128 + t;
+  uint32_t w[4] = {0, 0, 0, 0};
+  if (j < n_variants) {
+    const uint8_t* row = bed + j * bytes_per_variant;
+    const int64_t b0 = kc * 64 + piece * 16;
+    for (int b = 0; b < 16; ++b) {
+      if (b0 + b < bytes_per_variant) {
+        uint32_t x = row[b0 + b];
+        // PLINK 00->0, 01->missing(3), 10->1, 11->2 :  hi' = lo, lo' = lo ^ hi  per 2-bit field
+        const uint32_t lo = x & 0x55u, hi = (x >> 1) & 0x55u;
+        uint32_t y = ((lo) << 1) | (lo ^ hi);
+        // codes of samples >= n_samples (byte padding) -> 0
+        const int64_t s0 = (b0 + b) * 4;
+        for (int e = 0; e < 4; ++e)
+          if (s0 + e >= n_samples) y &= ~(3u << (2 * e));
+        w[b >> 2] |= y << (8 * (b & 3));
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(store + tile_offset(mp, kc, n_kc) + piece * 2048 + t * 16) =
+      make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// transpose: dst (Kd x M) unit (row g of dst, 64 codes along m) gathered from src; one thread per dst unit
+__global__ void store_transpose_kernel(const uint8_t* __restrict__ src, int64_t M, int64_t Kd, int64_t src_kc,
+                                       uint8_t* __restrict__ dst, int64_t dst_kc, int64_t n_units) {
+  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (unit >= n_units) return;
+  const int t = (int)(unit & 127);
+  const int piece = (int)((unit >> 7) & 3);
+  const int64_t tile = unit >> 9;
+  const int64_t kc = tile % dst_kc, mp = tile / dst_kc;
+  const int64_t g = mp * 128 + t;          // dst row = src contraction index
+  const int64_t m_first = kc * 256 + piece * 64;  // dst contraction = src row
+  uint32_t w[4] = {0, 0, 0, 0};
+  if (g < Kd) {
+    const int64_t s_kc = g >> 8;
+    const int s_b = (int)((g & 255) >> 2), s_sh = 2 * (int)(g & 3);
+    for (int e = 0; e < 64; ++e) {
+      const int64_t m = m_first + e;
+      if (m < M) {
+        const uint8_t byte = src[tile_offset(m >> 7, s_kc, src_kc) + (s_b >> 4) * 2048 + (m & 127) * 16 + (s_b & 15)];
+        w[e >> 4] |= (uint32_t)((byte >> s_sh) & 3u) << (2 * (e & 15));
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(dst + tile_offset(mp, kc, dst_kc) + piece * 2048 + t * 16) =
+      make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------------------------------------------ operand planes
+// one thread = one 16-byte unit of the image: fixed (K-block kb, half h, column n), 16 contraction positions.
+// byte e of the unit is MMA contraction index 16h + e, which the producers' decode maps to genotype position
+// 16h + (e>>2) + 4*(e&3) of the K-block (geno_mma.cuh decode16).
+__global__ void quantize_planes_kernel(const double* __restrict__ B, int64_t ldb, int64_t kd_limit, int K, int P, int N,
+                                       const double* __restrict__ mult, const double* __restrict__ row1,
+                                       const double* __restrict__ row2, int8_t* __restrict__ image1,
+                                       int8_t* __restrict__ image2, int64_t n_units) {
+  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (unit >= n_units) return;
+  const int n = (int)(unit % N);
+  const int64_t kbh = unit / N;
+  const int h = (int)(kbh & 1);
+  const int64_t kb = kbh >> 1;
+  uint32_t o1[4] = {0, 0, 0, 0}, o2[4] = {0, 0, 0, 0};
+  if (n < K * P) {
+    const int pl = n / K, k = n - pl * K;
+    const double mk = mult[k];
+    const double lim = ldexp(1.0, 8 * P - 2);
+#pragma unroll 4
+    for (int e = 0; e < 16; ++e) {
+      const int64_t g = kb * 32 + 16 * h + (e >> 2) + 4 * (e & 3);
+      if (g < kd_limit) {
+        double x = B[g * ldb + k] * mk;
+        if (row1) x *= row1[g];
+        for (int im = 0; im < 2; ++im) {
+          if (im == 1) {
+            if (!image2) break;
+            x *= row2[g];
+          }
+          double xc = fmin(fmax(x, -lim), lim);
+          long long qv = llrint(xc);
+          int d = 0;
+          for (int i = 0; i <= pl; ++i) {
+            d = (int)(signed char)(qv & 255);
+            qv = (qv - d) >> 8;
+          }
+          (im == 0 ? o1 : o2)[e >> 2] |= (uint32_t)(d & 255) << (8 * (e & 3));
+        }
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(image1 + unit * 16) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+  if (image2) *reinterpret_cast<uint4*>(image2 + unit * 16) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+}
+
+__global__ void colabsmax_kernel(const double* __restrict__ B, int64_t ldb, int64_t kd_limit, int K,
+                                 const double* __restrict__ row1, const double* __restrict__ row2,
+                                 unsigned long long* __restrict__ out, unsigned long long* __restrict__ out2) {
+  const int k = threadIdx.x % K, ry = threadIdx.x / K, rpb = blockDim.x / K;
+  if (ry >= rpb) return;
+  double m1 = 0.0, m2 = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * rpb + ry; r < kd_limit; r += (int64_t)gridDim.x * rpb) {
+    double v = fabs(B[r * ldb + k]);
+    if (row1) v *= fabs(row1[r]);
+    if (v != v) v = INFINITY;  // NaN poisons the scale so the caller can raise LinAlgError
+    m1 = fmax(m1, v);
+    if (row2) m2 = fmax(m2, v * fabs(row2[r]));
+  }
+  atomicMax(out + k, (unsigned long long)__double_as_longlong(m1));
+  if (row2) atomicMax(out2 + k, (unsigned long long)__double_as_longlong(m2));
+}
+
+__global__ void finalize_kernel(const long long* __restrict__ acc0, const long long* __restrict__ acc1, int64_t M, int K,
+                                const double* __restrict__ colscale, const double* __restrict__ rowa,
+                                const double* __restrict__ rowscale, const double* __restrict__ rowshift,
+                                const double* __restrict__ colshift, double* __restrict__ out, int64_t ldo) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * K) return;
+  const int64_t m = idx / K;
+  const int k = (int)(idx - m * K);
+  double v = (double)acc0[idx];
+  if (acc1) v += rowa[m] * (double)acc1[idx];
+  v *= colscale[k];
+  if (rowscale) v *= rowscale[m];
+  if (colshift) v += (rowshift ? rowshift[m] : 1.0) * colshift[k];
+  out[m * ldo + k] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ fp64 reductions
+constexpr int kGramRows = 128;     // rows per pass staged in smem
+constexpr int kGramMaxBlocks = 592;
+// stage 1: block b reduces rows {b, b+grid, ...}*kGramRows into work[b][K*K + K]
+__global__ void __launch_bounds__(256) gram_partial_kernel(const double* __restrict__ X, int64_t ldx,
+                                                           const double* __restrict__ Y, int64_t ldy, int64_t m, int K,
+                                                           double* __restrict__ work) {
+  extern __shared__ double sm[];
+  double* sx = sm;                     // [kGramRows][K]
+  double* sy = Y ? sm + kGramRows * K : sm;
+  const int n_out = K * K + K;
+  // each thread owns outputs o = tid, tid+256, ... (at most 4 for K <= 31; general loop otherwise)
+  const int tid = threadIdx.x;
+  constexpr int kMaxOwn = 68;  // supports K <= 128: (128*128+128)/256 = 64.5
+  double acc[kMaxOwn];
+  const int n_own = (n_out - tid + 255) / 256;
+  for (int i = 0; i < kMaxOwn; ++i) acc[i] = 0.0;
+  for (int64_t r0 = (int64_t)blockIdx.x * kGramRows; r0 < m; r0 += (int64_t)gridDim.x * kGramRows) {
+    const int rows = (int)min((int64_t)kGramRows, m - r0);
+    __syncthreads();
+    for (int i = tid; i < rows * K; i += 256) {
+      const int r = i / K, c = i - r * K;
+      sx[i] = X[(r0 + r) * ldx + c];
+      if (Y) sy[i] = Y[(r0 + r) * ldy + c];
+    }
+    __syncthreads();
+    for (int i = 0; i < n_own; ++i) {
+      const int o = tid + i * 256;
+      double a = acc[i];
+      if (o < K * K) {
+        const int e = o / K, f = o - e * K;
+        for (int r = 0; r < rows; ++r) a += sx[r * K + e] * sy[r * K + f];
+      } else {
+        const int e = o - K * K;
+        for (int r = 0; r < rows; ++r) a += sx[r * K + e];
+      }
+      acc[i] = a;
+    }
+  }
+  for (int i = 0; i < n_own; ++i) work[(size_t)blockIdx.x * n_out + tid + i * 256] = acc[i];
+}
+__global__ void gram_final_kernel(const double* __restrict__ work, int n_blocks, int K, double* __restrict__ G,
+                                  double* __restrict__ colsum) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_out = K * K + K;
+  if (o >= n_out) return;
+  double a = 0.0;
+  for (int b = 0; b < n_blocks; ++b) a += work[(size_t)b * n_out + o];
+  if (o < K * K)
+    G[o] = a;
+  else if (colsum)
+    colsum[o - K * K] = a;
+}
+
+__global__ void qvals_kernel(const double* __restrict__ si, const double* __restrict__ sj, int k, int scale,
+                             double* __restrict__ out) {
+  double d = 0, a = 0, b = 0;
+  for (int i = threadIdx.x; i < k; i += 32) {
+    const double x = si[i], y = sj[i];
+    d += (x - y) * (x - y);
+    a += x * x;
+    b += y * y;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (threadIdx.x == 0) {
+    double acc = sqrt(d);
+    if (scale) acc /= (sqrt(a) + sqrt(b)) / 2;
+    out[0] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) sqdiff_partial_kernel(const double* __restrict__ A, int64_t lda,
+                                                             const double* __restrict__ B, int64_t ldb,
+                                                             const double* __restrict__ s, int64_t m, int K,
+                                                             double* __restrict__ work) {
+  __shared__ double red[8];
+  double a = 0.0;
+  const int64_t total = m * K;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / K;
+    const int k = (int)(i - r * K);
+    const double d = A[r * lda + k] - B[r * ldb + k] * (s ? s[k] : 1.0);
+    a += d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    work[blockIdx.x] = t;
+  }
+}
+__global__ void sum_final_kernel(const double* __restrict__ work, int n, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < n; ++i) t += work[i];
+    out[0] = t;
+  }
+}
+
+}  // namespace lmdec
+
+// ================================================================================================ C ABI
+using namespace lmdec;
+
+extern "C" {
+
+const char* lmdec_last_error(void) { return g_err; }
+int lmdec_abi_version(void) { return 1; }
+
+int64_t lmdec_store_bytes(int64_t M, int64_t Kd) { return cdiv(M, 128) * cdiv(Kd, 256) * 8192; }
+int64_t lmdec_image_bytes(int64_t Kd, int N) { return cdiv(Kd, 256) * 8 * (int64_t)N * 32; }
+
+int lmdec_pack_2bit(const void* src, int dtype, int64_t stride_m, int64_t stride_kd, int64_t block_m, int64_t block_kd,
+                    int64_t m0, int64_t kd0, uint8_t* store, int64_t M, int64_t Kd, int32_t* bad_count, void* stream) {
+  if (m0 % 128 || kd0 % 256) return fail("lmdec_pack_2bit: m0 must be a multiple of 128 and kd0 of 256");
+  if (m0 + block_m > M || kd0 + block_kd > Kd || block_m <= 0 || block_kd <= 0)
+    return fail("lmdec_pack_2bit: block outside the store");
+  const int64_t n_kc = cdiv(Kd, 256);
+  const int64_t mp0 = m0 / 128, kc0 = kd0 / 256;
+  const int64_t n_mp_blk = cdiv(m0 + block_m, 128) - mp0, n_kc_blk = cdiv(kd0 + block_kd, 256) - kc0;
+  const int64_t n_units = n_mp_blk * n_kc_blk * 512;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)cdiv(n_units, threads);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LMDEC_PACK(T)                                                                                              \
+  pack_kernel<T><<<blocks, threads, 0, st>>>((const T*)src, stride_m, stride_kd, block_m, block_kd, m0, kd0, store, \
+                                             n_kc, mp0, kc0, n_mp_blk, n_kc_blk, bad_count)
+  switch (dtype) {
+    case LMDEC_I8: LMDEC_PACK(int8_t); break;
+    case LMDEC_U8: LMDEC_PACK(uint8_t); break;
+    case LMDEC_F32: LMDEC_PACK(float); break;
+    case LMDEC_F64: LMDEC_PACK(double); break;
+    default: return fail("lmdec_pack_2bit: unknown dtype");
+  }
+#undef LMDEC_PACK
+  return check_launch("lmdec_pack_2bit");
+}
+
+int lmdec_unpack_2bit(const uint8_t* store, int64_t M, int64_t Kd, int8_t* dst, int64_t ld, void* stream) {
+  const int64_t n_kc = cdiv(Kd, 256), n_units = cdiv(M, 128) * n_kc * 512;
+  unpack_kernel<<<(unsigned)cdiv(n_units, 256), 256, 0, (cudaStream_t)stream>>>(store, M, Kd, n_kc, dst, ld, n_units);
+  return check_launch("lmdec_unpack_2bit");
+}
+
+int lmdec_recode_bed(const uint8_t* bed, int64_t n_variants, int64_t n_samples, uint8_t* store, void* stream) {
+  const int64_t n_kc = cdiv(n_samples, 256), n_units = cdiv(n_variants, 128) * n_kc * 512;
+  recode_bed_kernel<<<(unsigned)cdiv(n_units, 256), 256, 0, (cudaStream_t)stream>>>(
+      bed, n_variants, n_samples, cdiv(n_samples, 4), store, n_kc, n_units);
+  return check_launch("lmdec_recode_bed");
+}
+
+int lmdec_store_transpose(const uint8_t* src, int64_t M, int64_t Kd, uint8_t* dst, void* stream) {
+  const int64_t src_kc = cdiv(Kd, 256), dst_kc = cdiv(M, 256), n_units = cdiv(Kd, 128) * dst_kc * 512;
+  store_transpose_kernel<<<(unsigned)cdiv(n_units, 256), 256, 0, (cudaStream_t)stream>>>(src, M, Kd, src_kc, dst, dst_kc,
+                                                                                        n_units);
+  return check_launch("lmdec_store_transpose");
+}
+
+int lmdec_code_counts(const uint8_t* store, int64_t M, int64_t Kd, int64_t kd_limit, int64_t* counts, void* stream) {
+  if (kd_limit < 0 || kd_limit > Kd) return fail("lmdec_code_counts: kd_limit outside the store");
+  code_counts_kernel<<<(unsigned)cdiv(M, 128), 128, 0, (cudaStream_t)stream>>>(store, M, cdiv(Kd, 256), kd_limit,
+                                                                              (long long*)counts);
+  return check_launch("lmdec_code_counts");
+}
+
+int lmdec_quantize_planes(const double* B, int64_t ldb, int64_t Kd, int64_t kd_limit, int K, int P, int N,
+                          const double* mult, const double* row1, const double* row2, int8_t* image1, int8_t* image2,
+                          void* stream) {
+  if (P < 1 || P > 4 || K < 1 || N % 16 || N < 16 || N > 128 || K * P > N)
+    return fail("lmdec_quantize_planes: need 1<=P<=4, N%16==0, 16<=N<=128, K*P<=N");
+  if (image2 && !row2) return fail("lmdec_quantize_planes: image2 needs row2");
+  if (kd_limit > Kd) return fail("lmdec_quantize_planes: kd_limit > Kd");
+  const int64_t n_units = cdiv(Kd, 256) * 8 * 2 * N;
+  quantize_planes_kernel<<<(unsigned)cdiv(n_units, 256), 256, 0, (cudaStream_t)stream>>>(
+      B, ldb, kd_limit, K, P, N, mult, row1, row2, image1, image2, n_units);
+  return check_launch("lmdec_quantize_planes");
+}
+
+int lmdec_colabsmax(const double* B, int64_t ldb, int64_t kd_limit, int K, const double* row1, const double* row2,
+                    double* out, double* out2, void* stream) {
+  if (K < 1 || K > 256) return fail("lmdec_colabsmax: K out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, K * sizeof(double), st);
+  if (row2) cudaMemsetAsync(out2, 0, K * sizeof(double), st);
+  const int rpb = 256 / K > 0 ? 256 / K : 1;
+  const int threads = K > 256 ? K : 256;
+  int64_t blocks = cdiv(kd_limit, rpb);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  colabsmax_kernel<<<(unsigned)blocks, threads, 0, st>>>(B, ldb, kd_limit, K, row1, row2, (unsigned long long*)out,
+                                                         (unsigned long long*)out2);
+  return check_launch("lmdec_colabsmax");
+}
+
+int lmdec_geno_matmul(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit, int has_missing,
+                      int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N, int64_t* out0,
+                      int64_t* out1, int splits, void* stream) {
+  if (N % 16 || N < 16 || N > 128 || K * P > N || P < 1 || P > 4) return fail("lmdec_geno_matmul: bad K/P/N");
+  if (m_limit <= 0 || m_limit > M || kd_limit <= 0 || kd_limit > Kd) return fail("lmdec_geno_matmul: bad limits");
+  if (mode == 1 && (!has_missing || !out1)) return fail("lmdec_geno_matmul: mode 1 needs has_missing and out1");
+  if (!image1 || !out0) return fail("lmdec_geno_matmul: null operand");
+  static thread_local int n_sm = 0;
+  static thread_local bool attr_set = false;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  GenoMmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.store = store;
+  p.store_kc = cdiv(Kd, 256);
+  p.m_limit = m_limit;
+  p.m_tiles = (int)cdiv(m_limit, 128);
+  p.n_chunks = (int)cdiv(kd_limit, 256);
+  p.has_missing = has_missing ? 1 : 0;
+  p.mode = mode;
+  p.n_img = (has_missing && mode == 0 && image2) ? 2 : 1;
+  p.image1 = image1;
+  p.image2 = image2;
+  p.K = K;
+  p.P = P;
+  p.N = N;
+  p.out0 = (long long*)out0;
+  p.out1 = (long long*)out1;
+  // split-K: aim at >= 2 work items per SM, keep >= 4 chunks per split, cap the int32 accumulators (|acc| < 2^30)
+  int want = splits;
+  if (want <= 0) {
+    want = 1;
+    if (p.m_tiles < 2 * n_sm) want = (int)cdiv(2 * n_sm, p.m_tiles);
+    const int max_by_len = p.n_chunks / 4 > 0 ? p.n_chunks / 4 : 1;
+    if (want > max_by_len) want = max_by_len;
+  }
+  const int min_splits = (int)cdiv(p.n_chunks, 8192);  // 8192 chunks * 256 * 2 * 128 = 2^29
+  if (want < min_splits) want = min_splits;
+  if (want > p.n_chunks) want = p.n_chunks;
+  const int cps = (int)cdiv(p.n_chunks, want);
+  p.splits = (int)cdiv(p.n_chunks, cps);
+  p.use_atomics = p.splits > 1;
+  const size_t stage_bytes = (size_t)8 * N * 32 * p.n_img;
+  const size_t staging = (size_t)128 * (N + 1) * 4;
+  int b_stages = (int)((200 * 1024 - staging) / stage_bytes);
+  if (b_stages > kMaxBStages) b_stages = kMaxBStages;
+  if (b_stages < 2) return fail("lmdec_geno_matmul: shared memory budget");
+  p.b_stages = b_stages;
+  const size_t smem = b_stages * stage_bytes + staging;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(geno_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return fail("lmdec_geno_matmul: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  if (p.use_atomics) {
+    cudaMemsetAsync(out0, 0, (size_t)m_limit * K * 8, st);
+    if (mode == 1) cudaMemsetAsync(out1, 0, (size_t)m_limit * K * 8, st);
+  }
+  const int n_work = p.m_tiles * p.splits;
+  const int grid = n_work < n_sm ? n_work : n_sm;
+  geno_mma_kernel<<<grid, kThreads, smem, st>>>(p);
+  return check_launch("lmdec_geno_matmul");
+}
+
+int lmdec_finalize(const int64_t* acc0, const int64_t* acc1, int64_t M, int K, const double* colscale,
+                   const double* rowa, const double* rowscale, const double* rowshift, const double* colshift,
+                   double* out, int64_t ldo, void* stream) {
+  if (acc1 && !rowa) return fail("lmdec_finalize: acc1 needs rowa");
+  finalize_kernel<<<(unsigned)cdiv(M * K, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const long long*)acc0, (const long long*)acc1, M, K, colscale, rowa, rowscale, rowshift, colshift, out, ldo);
+  return check_launch("lmdec_finalize");
+}
+
+static int gram_blocks(int64_t m) {
+  int64_t b = cdiv(m, kGramRows);
+  if (b > kGramMaxBlocks) b = kGramMaxBlocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+int64_t lmdec_gram_work_doubles(int64_t m, int K) { return (int64_t)gram_blocks(m) * (K * K + K); }
+
+int lmdec_gram(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t m, int K, double* G, double* colsum,
+               double* work, void* stream) {
+  if (K < 1 || K > 128) return fail("lmdec_gram: K out of range (1..128)");
+  const int nb = gram_blocks(m);
+  const size_t smem = (size_t)kGramRows * K * sizeof(double) * (Y ? 2 : 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_set = true;
+  }
+  gram_partial_kernel<<<nb, 256, smem, st>>>(X, ldx, Y, ldy, m, K, work);
+  gram_final_kernel<<<(unsigned)cdiv(K * K + K, 128), 128, 0, st>>>(work, nb, K, G, colsum);
+  return check_launch("lmdec_gram");
+}
+
+int lmdec_qvals(const double* si, const double* sj, int k, int scale, double* out, void* stream) {
+  qvals_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(si, sj, k, scale, out);
+  return check_launch("lmdec_qvals");
+}
+
+int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, const double* s, int64_t m, int K,
+                 double* out, double* work, void* stream) {
+  int64_t nb = cdiv(m * K, 256 * 8);
+  if (nb > 592) nb = 592;
+  if (nb < 1) nb = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  sqdiff_partial_kernel<<<(unsigned)nb, 256, 0, st>>>(A, lda, B, ldb_, s, m, K, work);
+  sum_final_kernel<<<1, 32, 0, st>>>(work, (int)nb, out);
+  return check_launch("lmdec_sqdiff");
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+"""GPU parity of the C-ABI kernels against exact integer / float64 NumPy arithmetic (bit-exact where integer)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _capi():
+    from lmdec_b200 import _capi
+    return _capi, _capi.load()
+
+
+def _geno(rng, n, p, miss=0.0):
+    maf = rng.uniform(0.05, 0.5, size=p)
+    g = rng.binomial(2, maf, size=(n, p)).astype(np.int8)
+    if miss:
+        g[rng.random((n, p)) < miss] = -1
+    return g
+
+
+def _pack(torch, capi, lib, g_dev, M, Kd, stride_m, stride_kd):
+    store = torch.empty(lib.lmdec_store_bytes(M, Kd), dtype=torch.uint8, device=g_dev.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=g_dev.device)
+    capi.check(lib.lmdec_pack_2bit(capi.ptr(g_dev), 0, stride_m, stride_kd, M, Kd, 0, 0, capi.ptr(store), M, Kd,
+                                   capi.ptr(bad), capi.stream_ptr()), "pack")
+    assert int(bad.item()) == 0
+    return store
+
+
+@pytest.mark.parametrize("n,p,miss", [(5, 7, 0.0), (130, 300, 0.1), (257, 1025, 0.05), (1000, 513, 0.0)])
+def test_pack_unpack_counts_transpose_bit_exact(cuda, n, p, miss):
+    import torch
+    capi, lib = _capi()
+    rng = np.random.default_rng(n * 1000 + p)
+    g = _geno(rng, n, p, miss)
+    gd = torch.from_numpy(g).to(cuda)
+    s_store = _pack(torch, capi, lib, gd, n, p, p, 1)      # sample-major
+    v_store = _pack(torch, capi, lib, gd, p, n, 1, p)      # SNP-major
+    out = torch.full((n, p), 9, dtype=torch.int8, device=cuda)
+    capi.check(lib.lmdec_unpack_2bit(capi.ptr(s_store), n, p, capi.ptr(out), p, capi.stream_ptr()))
+    assert np.array_equal(out.cpu().numpy(), g)
+    out_t = torch.full((p, n), 9, dtype=torch.int8, device=cuda)
+    capi.check(lib.lmdec_unpack_2bit(capi.ptr(v_store), p, n, capi.ptr(out_t), n, capi.stream_ptr()))
+    assert np.array_equal(out_t.cpu().numpy(), g.T)
+    # transpose of the sample-major store == SNP-major store, byte for byte
+    v2 = torch.empty_like(v_store)
+    capi.check(lib.lmdec_store_transpose(capi.ptr(s_store), n, p, capi.ptr(v2), capi.stream_ptr()))
+    assert torch.equal(v2, v_store)
+    # counts (full and a ragged prefix)
+    for lim in (n, max(1, n - 3), max(1, n // 2)):
+        cnt = torch.empty((p, 4), dtype=torch.int64, device=cuda)
+        capi.check(lib.lmdec_code_counts(capi.ptr(v_store), p, n, lim, capi.ptr(cnt), capi.stream_ptr()))
+        sub = g[:lim]
+        exp = np.stack([(sub == 0).sum(0), (sub == 1).sum(0), (sub == 2).sum(0), (sub == -1).sum(0)], axis=1)
+        assert np.array_equal(cnt.cpu().numpy(), exp)
+
+
+def _quantize(torch, capi, lib, B, kd_limit, K, P, N, mult, row1=None, row2=None):
+    Kd = B.shape[0]
+    nbytes = lib.lmdec_image_bytes(Kd, N)
+    im1 = torch.empty(nbytes, dtype=torch.int8, device=B.device)
+    im2 = torch.empty(nbytes, dtype=torch.int8, device=B.device) if row2 is not None else None
+    capi.check(lib.lmdec_quantize_planes(capi.ptr(B), B.stride(0), Kd, kd_limit, K, P, N, capi.ptr(mult),
+                                         capi.ptr(row1), capi.ptr(row2), capi.ptr(im1), capi.ptr(im2),
+                                         capi.stream_ptr()), "quantize")
+    return im1, im2
+
+
+@pytest.mark.parametrize("M,Kd,K,P,miss,mode,splits", [
+    (128, 256, 20, 3, 0.0, 0, 1),
+    (100, 300, 20, 3, 0.0, 0, 1),
+    (300, 1000, 20, 4, 0.0, 0, 0),
+    (300, 5000, 20, 3, 0.05, 0, 0),
+    (513, 2049, 30, 3, 0.05, 1, 1),
+    (2000, 700, 10, 2, 0.1, 1, 0),
+    (260, 40000, 20, 3, 0.05, 0, 7),
+    (1, 1, 1, 1, 0.0, 0, 1),
+    (40000, 260, 30, 4, 0.02, 1, 0),
+])
+def test_geno_matmul_exact(cuda, M, Kd, K, P, miss, mode, splits):
+    import torch
+    capi, lib = _capi()
+    rng = np.random.default_rng(M + 7 * Kd + K)
+    g = _geno(rng, M, Kd, miss)
+    gd = torch.from_numpy(g).to(cuda)
+    store = _pack(torch, capi, lib, gd, M, Kd, Kd, 1)
+    N = ((K * P + 15) // 16) * 16
+    B = rng.standard_normal((Kd, K))
+    r1 = rng.uniform(0.5, 2.0, size=Kd)
+    r2 = rng.uniform(0.0, 2.0, size=Kd)
+    Bd, r1d, r2d = (torch.from_numpy(a).to(cuda) for a in (B, r1, r2))
+    amax = torch.empty(K, dtype=torch.float64, device=cuda)
+    amax2 = torch.empty(K, dtype=torch.float64, device=cuda)
+    capi.check(lib.lmdec_colabsmax(capi.ptr(Bd), K, Kd, K, capi.ptr(r1d), capi.ptr(r2d), capi.ptr(amax),
+                                   capi.ptr(amax2), capi.stream_ptr()))
+    np.testing.assert_array_equal(amax.cpu().numpy(), np.abs(B * r1[:, None]).max(0))
+    np.testing.assert_array_equal(amax2.cpu().numpy(), np.abs(B * r1[:, None] * r2[:, None]).max(0))
+    scale = np.maximum(amax.cpu().numpy(), amax2.cpu().numpy())
+    mult = (2.0 ** (8 * P - 2)) / scale
+    multd = torch.from_numpy(mult).to(cuda)
+    has_missing = int(miss > 0)
+    two_images = has_missing and mode == 0
+    im1, im2 = _quantize(torch, capi, lib, Bd, Kd, K, P, N, multd, r1d, r2d if two_images else None)
+    out0 = torch.full((M, K), -7, dtype=torch.int64, device=cuda)
+    out1 = torch.full((M, K), -7, dtype=torch.int64, device=cuda)
+    capi.check(lib.lmdec_geno_matmul(capi.ptr(store), M, Kd, M, Kd, has_missing, mode, capi.ptr(im1), capi.ptr(im2),
+                                     K, P, N, capi.ptr(out0), capi.ptr(out1), splits, capi.stream_ptr()), "matmul")
+    torch.cuda.synchronize()
+    q1 = np.rint((B * r1[:, None]) * mult).astype(np.int64)
+    q2 = np.rint((B * r1[:, None]) * mult * r2[:, None]).astype(np.int64)
+    val = np.where(g < 0, 0, g).astype(np.int64)
+    ind = (g < 0).astype(np.int64)
+    if mode == 0:
+        exp0 = val @ q1 + (ind @ q2 if has_missing else 0)
+        assert np.array_equal(out0.cpu().numpy(), exp0)
+    else:
+        assert np.array_equal(out0.cpu().numpy(), val @ q1)
+        assert np.array_equal(out1.cpu().numpy(), ind @ q1)
+
+
+def test_geno_matmul_prefix_limits(cuda):
+    """row-prefix (m_limit) and contraction-prefix (kd_limit) arguments used by SuccessiveBatchedPowerMethod."""
+    import torch
+    capi, lib = _capi()
+    rng = np.random.default_rng(5)
+    M, Kd, K, P = 700, 1500, 20, 3
+    N = 64
+    g = _geno(rng, M, Kd, 0.05)
+    store = _pack(torch, capi, lib, torch.from_numpy(g).to(cuda), M, Kd, Kd, 1)
+    B = rng.standard_normal((Kd, K))
+    Bd = torch.from_numpy(B).to(cuda)
+    for m_lim, kd_lim in [(700, 1500), (301, 1500), (700, 777), (129, 33)]:
+        mult = np.full(K, (2.0 ** (8 * P - 2)) / np.abs(B[:kd_lim]).max())
+        multd = torch.from_numpy(mult).to(cuda)
+        im1, _ = _quantize(torch, capi, lib, Bd, kd_lim, K, P, N, multd)
+        out0 = torch.full((M, K), -7, dtype=torch.int64, device=cuda)
+        out1 = torch.full((M, K), -7, dtype=torch.int64, device=cuda)
+        capi.check(lib.lmdec_geno_matmul(capi.ptr(store), M, Kd, m_lim, kd_lim, 1, 1, capi.ptr(im1), None, K, P, N,
+                                         capi.ptr(out0), capi.ptr(out1), 0, capi.stream_ptr()))
+        q1 = np.rint(B[:kd_lim] * mult).astype(np.int64)
+        sub = g[:m_lim, :kd_lim]
+        assert np.array_equal(out0.cpu().numpy()[:m_lim], np.where(sub < 0, 0, sub).astype(np.int64) @ q1)
+        assert np.array_equal(out1.cpu().numpy()[:m_lim], (sub < 0).astype(np.int64) @ q1)
+        assert (out0.cpu().numpy()[m_lim:] == -7).all()
+
+
+def test_finalize_gram_qvals_sqdiff(cuda):
+    import torch
+    capi, lib = _capi()
+    rng = np.random.default_rng(11)
+    M, K = 1000, 20
+    a0 = rng.integers(-2 ** 40, 2 ** 40, size=(M, K))
+    a1 = rng.integers(-2 ** 30, 2 ** 30, size=(M, K))
+    cs, ra, rs, rsh, csh = (rng.standard_normal(s) for s in (K, M, M, M, K))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    out = torch.empty((M, K), dtype=torch.float64, device=cuda)
+    d = [t(a) for a in (a0, a1, cs, ra, rs, rsh, csh)]  # keep the device copies alive across the async call
+    capi.check(lib.lmdec_finalize(capi.ptr(d[0]), capi.ptr(d[1]), M, K, capi.ptr(d[2]), capi.ptr(d[3]),
+                                  capi.ptr(d[4]), capi.ptr(d[5]), capi.ptr(d[6]), capi.ptr(out), K,
+                                  capi.stream_ptr()))
+    exp = (a0 + ra[:, None] * a1) * cs * rs[:, None] + rsh[:, None] * csh
+    np.testing.assert_allclose(out.cpu().numpy(), exp, rtol=1e-14, atol=0)
+    for m in (1, 127, 5000, 200000):
+        X, Y = rng.standard_normal((m, K)), rng.standard_normal((m, K))
+        Xd, Yd = t(X), t(Y)
+        work = torch.empty(lib.lmdec_gram_work_doubles(m, K), dtype=torch.float64, device=cuda)
+        G = torch.empty((K, K), dtype=torch.float64, device=cuda)
+        cs_ = torch.empty(K, dtype=torch.float64, device=cuda)
+        capi.check(lib.lmdec_gram(capi.ptr(Xd), K, None, 0, m, K, capi.ptr(G), capi.ptr(cs_), capi.ptr(work),
+                                  capi.stream_ptr()))
+        np.testing.assert_allclose(G.cpu().numpy(), X.T @ X, rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(cs_.cpu().numpy(), X.sum(0), rtol=1e-12, atol=1e-9)
+        capi.check(lib.lmdec_gram(capi.ptr(Xd), K, capi.ptr(Yd), K, m, K, capi.ptr(G), None, capi.ptr(work),
+                                  capi.stream_ptr()))
+        np.testing.assert_allclose(G.cpu().numpy(), X.T @ Y, rtol=1e-12, atol=1e-9)
+        s = rng.uniform(0.5, 2, K)
+        sd = t(s)
+        o = torch.empty(1, dtype=torch.float64, device=cuda)
+        w2 = torch.empty(600, dtype=torch.float64, device=cuda)
+        capi.check(lib.lmdec_sqdiff(capi.ptr(Xd), K, capi.ptr(Yd), K, capi.ptr(sd), m, K, capi.ptr(o), capi.ptr(w2),
+                                    capi.stream_ptr()))
+        np.testing.assert_allclose(o.item(), ((X - Y * s) ** 2).sum(), rtol=1e-12)
+    si, sj = rng.uniform(1, 2, 10), rng.uniform(1, 2, 10)
+    o = torch.empty(1, dtype=torch.float64, device=cuda)
+    sid, sjd = t(si), t(sj)
+    capi.check(lib.lmdec_qvals(capi.ptr(sid), capi.ptr(sjd), 10, 1, capi.ptr(o), capi.stream_ptr()))
+    exp = np.linalg.norm(si - sj) / ((np.linalg.norm(si) + np.linalg.norm(sj)) / 2)
+    np.testing.assert_allclose(o.item(), exp, rtol=1e-14)
+
+
+def test_recode_bed_matches_plink_code_map(cuda):
+    import torch
+    capi, lib = _capi()
+    rng = np.random.default_rng(3)
+    n_var, n_samp = 300, 1003
+    codes = rng.integers(0, 4, size=(n_var, n_samp)).astype(np.uint8)       # PLINK 2-bit codes
+    bpv = (n_samp + 3) // 4
+    padded = np.zeros((n_var, bpv * 4), dtype=np.uint8)
+    padded[:, :n_samp] = codes
+    padded[:, n_samp:] = 1  # garbage in the byte padding must be ignored
+    bed = (padded[:, 0::4] | (padded[:, 1::4] << 2) | (padded[:, 2::4] << 4) | (padded[:, 3::4] << 6)).astype(np.uint8)
+    store = torch.empty(lib.lmdec_store_bytes(n_var, n_samp), dtype=torch.uint8, device=cuda)
+    bed_d = torch.from_numpy(bed).to(cuda)
+    capi.check(lib.lmdec_recode_bed(capi.ptr(bed_d), n_var, n_samp, capi.ptr(store), capi.stream_ptr()))
+    out = torch.empty((n_var, n_samp), dtype=torch.int8, device=cuda)
+    capi.check(lib.lmdec_unpack_2bit(capi.ptr(store), n_var, n_samp, capi.ptr(out), n_samp, capi.stream_ptr()))
+    plink_to_dosage = np.array([0, -1, 1, 2], dtype=np.int8)   # 00 hom-A1, 01 missing, 10 het, 11 hom-A2
+    assert np.array_equal(out.cpu().numpy(), plink_to_dosage[codes])
+    cnt = torch.empty((n_var, 4), dtype=torch.int64, device=cuda)
+    capi.check(lib.lmdec_code_counts(capi.ptr(store), n_var, n_samp, n_samp, capi.ptr(cnt), capi.stream_ptr()))
+    assert int(cnt.sum().item()) == n_var * n_samp
