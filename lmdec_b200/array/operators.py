@@ -1,0 +1,169 @@
+"""Device-side leaves of the operator protocol: dense float matrices, sparse matrices, vectors.
+
+``as_operator`` is the ``da.array(data)`` coercion of the drivers (lmdec/decomp/iter_methods.py:357,543): Stacked /
+Chained / ScaledCenter / genotype operators are kept, everything else becomes a dense device matrix whose products are
+plain library GEMMs (cuBLAS through torch) in float64.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..device import F64, DeviceArray, as_tensor, require_cuda
+
+
+class DenseOperator:
+    """A [n, p] floating matrix resident in HBM."""
+
+    ndim = 2
+    group = None
+
+    def __init__(self, a, device=None, keep_dtype: bool = False):
+        device = device or require_cuda()
+        if isinstance(a, DeviceArray):
+            a = a.t
+        if isinstance(a, torch.Tensor):
+            t = a.to(device)
+        else:
+            arr = np.asarray(a)
+            if arr.dtype == object:
+                raise TypeError("object arrays are not supported")
+            t = torch.as_tensor(np.ascontiguousarray(arr), device=device)
+        if not (keep_dtype and t.dtype == torch.float32):
+            t = t.to(F64)
+        if t.ndim != 2:
+            raise ValueError("expected a 2-D array")
+        self.a = t
+
+    @property
+    def shape(self):
+        return tuple(self.a.shape)
+
+    @property
+    def local_rows(self):
+        return self.a.shape[0]
+
+    @property
+    def T(self):
+        out = DenseOperator.__new__(DenseOperator)
+        out.a = self.a.T
+        return out
+
+    def dot_t(self, x):
+        if x.shape[0] != self.a.shape[1]:
+            raise ValueError("shapes {} and {} not aligned".format(self.shape, tuple(x.shape)))
+        return (self.a @ x.to(self.a.dtype)).to(F64)
+
+    def tdot_t(self, y):
+        if y.shape[0] != self.a.shape[0]:
+            raise ValueError("shapes {} and {} not aligned".format(self.shape[::-1], tuple(y.shape)))
+        return (self.a.T @ y.to(self.a.dtype)).to(F64)
+
+    def dot(self, x):
+        return DeviceArray(self.dot_t(as_tensor(x, self.a.device)))
+
+    def __getitem__(self, item):
+        if isinstance(item, tuple):
+            item = tuple(torch.as_tensor(i, device=self.a.device) if isinstance(i, np.ndarray) else i for i in item)
+        elif isinstance(item, np.ndarray):
+            item = torch.as_tensor(item, device=self.a.device)
+        sub = self.a[item]
+        out = DenseOperator.__new__(DenseOperator)
+        out.a = sub if sub.ndim == 2 else sub.reshape(1, -1)
+        return out
+
+    def to_dense(self):
+        return self.a.to(F64)
+
+    def compute(self):
+        return self.a.cpu().numpy()
+
+    def persist(self):
+        return self
+
+    def rechunk(self, *a, **k):
+        return self
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.compute()
+        return a.astype(dtype) if dtype is not None else a
+
+
+class SparseOperator:
+    """scipy.sparse / pydata-sparse matrix on the device (the COO mask member of the reference's StackedArray,
+    lmdec/decomp/utils.py:185-188)."""
+
+    ndim = 2
+    group = None
+
+    def __init__(self, a, device=None):
+        import scipy.sparse as sp
+        device = device or require_cuda()
+        if not sp.issparse(a):
+            if hasattr(a, "tocsr"):
+                a = a.tocsr()
+            elif hasattr(a, "to_scipy_sparse"):
+                a = a.to_scipy_sparse()
+            else:
+                raise TypeError("not a sparse matrix")
+        csr = a.tocsr().astype(np.float64)
+        self.shape = tuple(csr.shape)
+        self._host = csr
+        self.a = torch.sparse_csr_tensor(torch.as_tensor(csr.indptr.astype(np.int64)),
+                                         torch.as_tensor(csr.indices.astype(np.int64)),
+                                         torch.as_tensor(csr.data), size=csr.shape, dtype=F64).to(device)
+        csc_t = a.T.tocsr().astype(np.float64)
+        self.at = torch.sparse_csr_tensor(torch.as_tensor(csc_t.indptr.astype(np.int64)),
+                                          torch.as_tensor(csc_t.indices.astype(np.int64)),
+                                          torch.as_tensor(csc_t.data), size=csc_t.shape, dtype=F64).to(device)
+
+    @property
+    def local_rows(self):
+        return self.shape[0]
+
+    @property
+    def T(self):
+        return SparseOperator(self._host.T, device=self.a.device)
+
+    def dot_t(self, x):
+        return self.a @ x if x.ndim == 2 else (self.a @ x[:, None])[:, 0]
+
+    def tdot_t(self, y):
+        return self.at @ y if y.ndim == 2 else (self.at @ y[:, None])[:, 0]
+
+    def dot(self, x):
+        return DeviceArray(self.dot_t(as_tensor(x, self.a.device)))
+
+    def __getitem__(self, item):
+        return SparseOperator(self._host[item], device=self.a.device)
+
+    def to_dense(self):
+        return self.a.to_dense()
+
+    def compute(self):
+        return np.asarray(self._host.todense())
+
+
+def is_sparse(a) -> bool:
+    """lmdec/array/utils.py:6-26"""
+    try:
+        import scipy.sparse as sp
+        if sp.issparse(a):
+            return True
+    except ImportError:  # pragma: no cover
+        pass
+    return type(a).__module__.split(".")[0] == "sparse" or isinstance(a, SparseOperator)
+
+
+def as_operator(data, device=None):
+    from ..store import GenotypeOperator, _Transposed
+    from .chained import ChainedArray
+    from .scaled_legacy import ScaledCenterArray
+    from .stacked import StackedArray
+    if isinstance(data, (GenotypeOperator, _Transposed, StackedArray, ChainedArray, ScaledCenterArray, DenseOperator,
+                         SparseOperator)):
+        return data
+    if is_sparse(data):
+        return SparseOperator(data, device=device)
+    op = DenseOperator(data, device=device, keep_dtype=True)
+    return op

@@ -1,0 +1,166 @@
+"""Device plumbing: torch owns HBM and streams, the C ABI does the arithmetic.
+
+``DeviceArray`` is what the drop-in API returns where the reference returns a dask array: it exposes ``shape``,
+``T``, slicing, ``compute()``/``persist()`` and ``__array__`` (reference usage: tests/test_iter_methods.py:81,
+lmdec/decomp/iter_methods.py:408-417) while keeping the data resident on the GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _capi
+
+F64 = torch.float64
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("lmdec_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class DeviceArray:
+    """Thin array-like view of a CUDA tensor (float64 unless stated)."""
+
+    __array_priority__ = 100
+
+    def __init__(self, t: torch.Tensor):
+        self.t = t
+
+    # -- dask-like surface
+    @property
+    def shape(self):
+        return tuple(self.t.shape)
+
+    @property
+    def ndim(self):
+        return self.t.ndim
+
+    @property
+    def dtype(self):
+        return np.dtype(str(self.t.dtype).replace("torch.", ""))
+
+    @property
+    def T(self):
+        return DeviceArray(self.t.T)
+
+    def compute(self):
+        return self.t.detach().cpu().numpy()
+
+    def persist(self):
+        return self
+
+    def rechunk(self, *a, **k):
+        return self
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.compute()
+        return a.astype(dtype) if dtype is not None else a
+
+    def __len__(self):
+        return self.t.shape[0]
+
+    def __getitem__(self, item):
+        if isinstance(item, np.ndarray):
+            item = torch.as_tensor(item, device=self.t.device)
+        elif isinstance(item, tuple):
+            item = tuple(torch.as_tensor(i, device=self.t.device) if isinstance(i, np.ndarray) else i for i in item)
+        return DeviceArray(self.t[item])
+
+    def dot(self, other):
+        return DeviceArray(self.t @ as_tensor(other, self.t.device))
+
+    # -- arithmetic used on S / U / V by callers
+    def _bin(self, other, op):
+        o = other.t if isinstance(other, DeviceArray) else other
+        if isinstance(o, np.ndarray):
+            o = torch.as_tensor(o, device=self.t.device)
+        return DeviceArray(op(self.t, o))
+
+    def __add__(self, o): return self._bin(o, torch.add)
+    def __sub__(self, o): return self._bin(o, torch.sub)
+    def __mul__(self, o): return self._bin(o, torch.mul)
+    def __truediv__(self, o): return self._bin(o, torch.div)
+    def __pow__(self, o): return self._bin(o, torch.pow)
+    def __neg__(self): return DeviceArray(-self.t)
+    __radd__ = __add__
+    __rmul__ = __mul__
+
+    def __repr__(self):
+        return f"DeviceArray(shape={self.shape}, dtype={self.t.dtype}, device={self.t.device})"
+
+
+def as_tensor(x, device=None, dtype=F64) -> torch.Tensor:
+    """Anything array-like -> CUDA tensor of ``dtype`` (no copy when already there)."""
+    device = device or require_cuda()
+    if isinstance(x, DeviceArray):
+        x = x.t
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype)
+    a = np.asarray(x)
+    if a.dtype == object:
+        raise TypeError("cannot move an object array to the device")
+    return torch.as_tensor(np.ascontiguousarray(a), device=device).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# thin wrappers over the C ABI (all asynchronous on the current torch stream)
+# ------------------------------------------------------------------------------------------------------------------
+_WORK = {}
+
+
+def _work(device, n: int) -> torch.Tensor:
+    key = (device, "f64")
+    w = _WORK.get(key)
+    if w is None or w.numel() < n:
+        w = torch.empty(max(n, 1 << 16), dtype=F64, device=device)
+        _WORK[key] = w
+    return w
+
+
+def _rows(x: torch.Tensor) -> torch.Tensor:
+    """row-major with unit inner stride (the kernels take a leading dimension)."""
+    if x.ndim != 2:
+        raise ValueError("expected a 2-D operand")
+    if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+        x = x.contiguous()
+    return x
+
+
+def gram(x: torch.Tensor, y: torch.Tensor = None, want_colsum: bool = False):
+    """G = x^T x (or x^T y) [K,K] and optionally the column sums of x; deterministic."""
+    lib = _capi.load()
+    x = _rows(x)
+    m, K = x.shape
+    if K > 128:  # outside the kernel's range: plain library GEMM
+        g = x.T @ (x if y is None else y)
+        return (g, x.sum(0)) if want_colsum else g
+    yy = None if y is None else _rows(y)
+    G = torch.empty((K, K), dtype=F64, device=x.device)
+    cs = torch.empty(K, dtype=F64, device=x.device) if want_colsum else None
+    work = _work(x.device, lib.lmdec_gram_work_doubles(m, K))
+    _capi.check(lib.lmdec_gram(_capi.ptr(x), x.stride(0), _capi.ptr(yy), 0 if yy is None else yy.stride(0), m, K,
+                               _capi.ptr(G), _capi.ptr(cs), _capi.ptr(work), _capi.stream_ptr()), "lmdec_gram")
+    return (G, cs) if want_colsum else G
+
+
+def qvals(si: torch.Tensor, sj: torch.Tensor, scale: bool = True) -> torch.Tensor:
+    lib = _capi.load()
+    out = torch.empty(1, dtype=F64, device=si.device)
+    si, sj = si.contiguous(), sj.contiguous()
+    _capi.check(lib.lmdec_qvals(_capi.ptr(si), _capi.ptr(sj), si.numel(), int(bool(scale)), _capi.ptr(out),
+                                _capi.stream_ptr()), "lmdec_qvals")
+    return out
+
+
+def sqdiff(a: torch.Tensor, b: torch.Tensor, s: torch.Tensor = None) -> torch.Tensor:
+    """sum (a - b*s)^2, deterministic two-stage reduction."""
+    lib = _capi.load()
+    a, b = _rows(a), _rows(b)
+    out = torch.empty(1, dtype=F64, device=a.device)
+    work = _work(a.device, 1024)
+    sc = None if s is None else s.contiguous()
+    _capi.check(lib.lmdec_sqdiff(_capi.ptr(a), a.stride(0), _capi.ptr(b), b.stride(0), _capi.ptr(sc), a.shape[0],
+                                 a.shape[1], _capi.ptr(out), _capi.ptr(work), _capi.stream_ptr()), "lmdec_sqdiff")
+    return out

@@ -1,0 +1,401 @@
+"""Device-resident genotype storage and the lazily centred / scaled / mean-imputed operator over it.
+
+Replaces the dask chunk graph the reference builds in ``make_snp_array`` (lmdec/decomp/utils.py:195-289):
+
+    SNP = Chained[ Stacked[ Stacked[G(int8, NaN->0), M(sparse COO of column means at the NaNs)], -mean ], 1/std ]
+
+Here G and the NaN positions live together in a 2-bit tile store (codes 0,1,2 and 3 = missing), held twice
+(sample-major for ``A.dot``, SNP-major -- the .bed orientation -- for ``A.T.dot``), and the algebra of
+``StackedArray.dot`` / ``ChainedArray.dot`` (lmdec/array/stacked.py:172-217, chained.py:169-177) is folded into the
+small operands:
+
+    A.dot(t)    = G (D t) + I (mu o D t) - 1 (mu^T D t)          I = missing indicator
+    A.T.dot(y)  = D ( G^T y + mu o (I^T y) - mu (1^T y) )
+
+The two big products run exactly (int64) on the tensor cores: the float64 operand is split into P signed-byte planes
+(fixed point, 8P-2 bits below its column maximum), see ``csrc/geno_mma.cuh``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _capi
+from .device import F64, DeviceArray, as_tensor, require_cuda
+
+_DTYPE_CODE = {torch.int8: 0, torch.uint8: 1, torch.float32: 2, torch.float64: 3}
+
+
+def _round16(x: int) -> int:
+    return (x + 15) // 16 * 16
+
+
+class GenotypeStore:
+    """n x p genotypes (rows = samples) as two 2-bit tile stores on one GPU.
+
+    ``row_offset`` / ``n_global`` describe the shard when samples are row-sharded over ranks (one process per GPU);
+    moments are then computed from the all-reduced integer counts, so every rank holds identical mean / std.
+    """
+
+    def __init__(self, n: int, p: int, device=None, group=None, n_global: Optional[int] = None, row_offset: int = 0):
+        self.lib = _capi.load()
+        self.device = device or require_cuda()
+        self.n, self.p = int(n), int(p)
+        self.group = group
+        self.n_global = int(n_global) if n_global is not None else self.n
+        self.row_offset = int(row_offset)
+        self.s_store = torch.zeros(self.lib.lmdec_store_bytes(self.n, self.p), dtype=torch.uint8, device=self.device)
+        self.v_store = torch.zeros(self.lib.lmdec_store_bytes(self.p, self.n), dtype=torch.uint8, device=self.device)
+        self._bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._counts = None
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_dense(cls, array, device=None, rows_per_block: int = 8192, group=None, n_global=None, row_offset=0):
+        """Pack a dense {0,1,2,NaN} matrix (NumPy or torch; int8/uint8/float32/float64; integer missing = -1 or 3).
+
+        Host arrays are streamed to the device in row blocks through a pinned staging buffer, so the dense matrix is
+        never resident in HBM as a whole.
+        """
+        if isinstance(array, DeviceArray):
+            array = array.t
+        if not isinstance(array, torch.Tensor):
+            array = np.asarray(array)
+            if array.dtype not in (np.int8, np.uint8, np.float32, np.float64):
+                array = array.astype(np.float64)
+            array = torch.from_numpy(np.ascontiguousarray(array))
+        if array.ndim != 2:
+            raise ValueError("expected a 2-D genotype matrix")
+        if array.dtype not in _DTYPE_CODE:
+            array = array.to(torch.float64)
+        n, p = array.shape
+        self = cls(n, p, device=device, group=group, n_global=n_global, row_offset=row_offset)
+        rows_per_block = max(256, rows_per_block // 256 * 256)
+        for r0 in range(0, n, rows_per_block):
+            blk = array[r0:r0 + rows_per_block]
+            if blk.device != self.device:
+                blk = blk.contiguous().pin_memory().to(self.device, non_blocking=True) if blk.device.type == "cpu" \
+                    else blk.to(self.device)
+            self.pack_rows(blk, r0)
+        self.finish()
+        return self
+
+    def pack_rows(self, block: torch.Tensor, r0: int):
+        """Write rows [r0, r0+len(block)) (r0 a multiple of 256) of both stores from a device block."""
+        if r0 % 256:
+            raise ValueError("row blocks must start at a multiple of 256")
+        if block.stride(1) != 1:
+            block = block.contiguous()
+        nb, p = block.shape
+        code = _DTYPE_CODE[block.dtype]
+        st = _capi.stream_ptr()
+        ld = block.stride(0)
+        _capi.check(self.lib.lmdec_pack_2bit(_capi.ptr(block), code, ld, 1, nb, p, r0, 0, _capi.ptr(self.s_store),
+                                             self.n, self.p, _capi.ptr(self._bad), st), "pack (sample-major)")
+        _capi.check(self.lib.lmdec_pack_2bit(_capi.ptr(block), code, 1, ld, p, nb, 0, r0, _capi.ptr(self.v_store),
+                                             self.p, self.n, _capi.ptr(self._bad), st), "pack (SNP-major)")
+        self._counts = None
+
+    @classmethod
+    def from_bed_bytes(cls, bed, n_samples: int, n_variants: int, device=None):
+        """PLINK .bed payload (variant-major, after the 3-byte magic) -> store, without a float round trip.
+        Replaces pandas_plink.read_plink under load_plink_array (lmdec/array/io.py:16-73).  Code map (the one
+        pandas_plink uses): 00 -> 0, 01 -> missing, 10 -> 1, 11 -> 2."""
+        self = cls(n_samples, n_variants, device=device)
+        bed_t = bed if isinstance(bed, torch.Tensor) else torch.from_numpy(np.frombuffer(bed, dtype=np.uint8).copy())
+        bed_t = bed_t.to(self.device)
+        if bed_t.numel() != n_variants * ((n_samples + 3) // 4):
+            raise ValueError("bed payload size does not match n_variants x ceil(n_samples/4)")
+        st = _capi.stream_ptr()
+        _capi.check(self.lib.lmdec_recode_bed(_capi.ptr(bed_t), n_variants, n_samples, _capi.ptr(self.v_store), st))
+        _capi.check(self.lib.lmdec_store_transpose(_capi.ptr(self.v_store), n_variants, n_samples,
+                                                   _capi.ptr(self.s_store), st))
+        self.finish()
+        return self
+
+    def finish(self):
+        bad = int(self._bad.item())
+        if bad:
+            raise ValueError("genotype matrix holds values other than 0, 1, 2 and NaN")
+        return self
+
+    # ------------------------------------------------------------------ exact integer content
+    def code_counts(self, rows: Optional[int] = None) -> torch.Tensor:
+        """int64 [p, 4]: per SNP the number of samples with dosage 0, 1, 2 and missing (all ranks summed)."""
+        full = rows is None
+        if full and self._counts is not None:
+            return self._counts
+        lim = self.n if full else int(rows)
+        cnt = torch.empty((self.p, 4), dtype=torch.int64, device=self.device)
+        _capi.check(self.lib.lmdec_code_counts(_capi.ptr(self.v_store), self.p, self.n, lim, _capi.ptr(cnt),
+                                               _capi.stream_ptr()), "code_counts")
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(cnt, group=self.group)
+        if full:
+            self._counts = cnt
+        return cnt
+
+    @property
+    def has_missing(self) -> bool:
+        return bool((self.code_counts()[:, 3].sum() > 0).item())
+
+    def to_dense(self, transpose: bool = False, rows: Optional[int] = None) -> torch.Tensor:
+        """int8 [n, p] (or [p, n]) with -1 at missing: the bit-exact decode used by the parity tests.
+        `rows` limits the decode to a leading block of store rows."""
+        M, Kd, st = (self.p, self.n, self.v_store) if transpose else (self.n, self.p, self.s_store)
+        if rows is not None:
+            M = min(M, int(rows))
+        out = torch.empty((M, Kd), dtype=torch.int8, device=self.device)
+        _capi.check(self.lib.lmdec_unpack_2bit(_capi.ptr(st), M, Kd, _capi.ptr(out), Kd, _capi.stream_ptr()))
+        return out
+
+    def moments(self, std_method: str = "binom"):
+        """(mean, std) float64 [p] from the integer counts: get_array_moments (lmdec/decomp/utils.py:64-82)."""
+        c = self.code_counts().to(F64)
+        cnt = c[:, 0] + c[:, 1] + c[:, 2]
+        mean = (c[:, 1] + 2.0 * c[:, 2]) / cnt
+        if std_method == "binom":
+            u = mean / 2
+            std = torch.sqrt(2 * u * (1 - u))
+        elif std_method in ("norm", "normal"):
+            var = (c[:, 0] * mean ** 2 + c[:, 1] * (1 - mean) ** 2 + c[:, 2] * (2 - mean) ** 2) / cnt
+            std = torch.sqrt(var)
+        else:
+            raise NotImplementedError(f"std_method, {std_method}, is not implemented ")
+        return mean, std
+
+
+class GenotypeOperator:
+    """The operator ``make_snp_array`` returns: ((G + M) - 1 mean^T) diag(1/std), evaluated on the tensor cores.
+
+    Operator protocol used by the decomposition drivers: ``shape``, ``dot``, ``T.dot``, row-prefix
+    slicing ``[0:m, :]`` (moments are NOT refit on a prefix, as in the reference: lmdec/array/chained.py:235-241,
+    stacked.py:254-265), fancy row indexing raises ``NotImplementedError`` like ``ChainedArray.__getitem__``.
+    """
+
+    def __init__(self, store: GenotypeStore, mean: Optional[torch.Tensor], inv_std: Optional[torch.Tensor],
+                 planes: int = 3, rows: Optional[int] = None, impute: bool = True):
+        self.store = store
+        self.mean = mean            # centring vector (None = no centring)
+        self.inv_std = inv_std      # scaling vector (None = no scaling)
+        self.planes = int(planes)
+        self.rows = store.n if rows is None else int(rows)   # local row prefix
+        self.has_missing = store.has_missing
+        if self.has_missing and not impute:
+            raise ValueError("the store holds missing genotypes; they are always mean-imputed")
+        self.impute_mean = store.moments()[0] if self.has_missing else None
+        self._t = None
+        self._buf = {}
+
+    # ------------------------------------------------------------------ protocol
+    @property
+    def shape(self):
+        n = self.rows if self.store.group is None else self._global_rows()
+        return (n, self.store.p)
+
+    def _global_rows(self):
+        if self.rows == self.store.n:
+            return self.store.n_global
+        import torch.distributed as dist
+        t = torch.tensor([self.rows], dtype=torch.int64, device=self.store.device)
+        dist.all_reduce(t, group=self.store.group)
+        return int(t.item())
+
+    @property
+    def local_rows(self):
+        return self.rows
+
+    ndim = 2
+
+    @property
+    def T(self):
+        if self._t is None:
+            self._t = _Transposed(self)
+        return self._t
+
+    def dot(self, x):
+        return DeviceArray(self.dot_t(as_tensor(x, self.store.device)))
+
+    def persist(self):
+        return self
+
+    def rechunk(self, *a, **k):
+        return self
+
+    def __getitem__(self, item):
+        if not isinstance(item, tuple):
+            item = (item, slice(None))
+        if len(item) != 2 or item[1] != slice(None, None, None):
+            raise NotImplementedError("only row selection [rows, :] is supported")
+        r = item[0]
+        if not isinstance(r, slice):
+            raise NotImplementedError("Only implements slice indexing")
+        start, stop, step = r.indices(self.shape[0])
+        if start != 0 or step != 1:
+            raise NotImplementedError("only row prefixes [0:m, :] are views of the store")
+        if self.store.group is not None:
+            # block-contiguous shards: the global prefix [0, stop) is this rank's [0, clamp(stop - offset)]
+            stop = min(max(stop - self.store.row_offset, 0), self.store.n)
+        op = GenotypeOperator.__new__(GenotypeOperator)
+        op.__dict__.update(self.__dict__)
+        op.rows, op._t, op._buf = stop, None, self._buf
+        return op
+
+    # ------------------------------------------------------------------ buffers
+    def _buffers(self, tag, Kd, M, K, two_images, two_outs):
+        P = self.planes
+        N = _round16(K * P)
+        if N > 128:
+            raise ValueError(f"k + buffer = {K} with {P} planes needs N = {N} > 128 tensor-core columns; "
+                             "lower `planes` or k + buffer")
+        key = (tag, K, P)
+        b = self._buf.get(key)
+        if b is None:
+            dev = self.store.device
+            nbytes = self.store.lib.lmdec_image_bytes(Kd, N)
+            b = {
+                "N": N,
+                "im1": torch.empty(nbytes, dtype=torch.int8, device=dev),
+                "im2": torch.empty(nbytes, dtype=torch.int8, device=dev) if two_images else None,
+                "out0": torch.empty((M, K), dtype=torch.int64, device=dev),
+                "out1": torch.empty((M, K), dtype=torch.int64, device=dev) if two_outs else None,
+                "amax": torch.empty(K, dtype=F64, device=dev),
+                "amax2": torch.empty(K, dtype=F64, device=dev),
+            }
+            self._buf[key] = b
+        return b
+
+    def _mult(self, b, two):
+        s = torch.maximum(b["amax"], b["amax2"]) if two else b["amax"]
+        lim = float(2.0 ** (8 * self.planes - 2))
+        # a zero column quantises to zero with any multiplier; inf/NaN columns poison the result on purpose
+        return torch.where(s > 0, lim / s, torch.ones_like(s))
+
+    # ------------------------------------------------------------------ the two products (torch tensors in/out)
+    def dot_t(self, t: torch.Tensor) -> torch.Tensor:
+        """x[n_local, K] = A t  for t [p, K] float64 on the device."""
+        squeeze = t.ndim == 1
+        if squeeze:
+            t = t[:, None]
+        st, lib = self.store, self.store.lib
+        if t.shape[0] != st.p:
+            raise ValueError("shapes {} and {} not aligned".format(self.shape, tuple(t.shape)))
+        t = t.contiguous()
+        K = t.shape[1]
+        miss = self.has_missing
+        b = self._buffers("dot", st.p, st.n, K, miss, False)
+        sp = _capi.stream_ptr()
+        d, mu = self.inv_std, self.impute_mean
+        _capi.check(lib.lmdec_colabsmax(_capi.ptr(t), K, st.p, K, _capi.ptr(d), _capi.ptr(mu) if miss else None,
+                                        _capi.ptr(b["amax"]), _capi.ptr(b["amax2"]), sp), "colabsmax")
+        mult = self._mult(b, miss)
+        _capi.check(lib.lmdec_quantize_planes(_capi.ptr(t), K, st.p, st.p, K, self.planes, b["N"], _capi.ptr(mult),
+                                              _capi.ptr(d), _capi.ptr(mu) if miss else None, _capi.ptr(b["im1"]),
+                                              _capi.ptr(b["im2"]) if miss else None, sp), "quantize")
+        m = self.rows
+        x = torch.empty((m, K), dtype=F64, device=st.device)
+        if m == 0:
+            return x[:, 0] if squeeze else x
+        _capi.check(lib.lmdec_geno_matmul(_capi.ptr(st.s_store), st.n, st.p, m, st.p, int(miss), 0,
+                                          _capi.ptr(b["im1"]), _capi.ptr(b["im2"]) if miss else None, K, self.planes,
+                                          b["N"], _capi.ptr(b["out0"]), None, 0, sp), "geno_matmul (A.dot)")
+        colscale = 1.0 / mult
+        colshift = None
+        if self.mean is not None:
+            w = self.mean if d is None else self.mean * d
+            colshift = -(w @ t)
+        _capi.check(lib.lmdec_finalize(_capi.ptr(b["out0"]), None, m, K, _capi.ptr(colscale), None, None, None,
+                                       _capi.ptr(colshift), _capi.ptr(x), K, sp), "finalize")
+        return x[:, 0] if squeeze else x
+
+    def tdot_t(self, y: torch.Tensor) -> torch.Tensor:
+        """w[p, K] = A^T y  for y [n_local, K] float64 on the device (all-reduced over ranks when sharded)."""
+        squeeze = y.ndim == 1
+        if squeeze:
+            y = y[:, None]
+        st, lib = self.store, self.store.lib
+        m = self.rows
+        if y.shape[0] != m:
+            raise ValueError("shapes {} and {} not aligned".format(self.shape[::-1], tuple(y.shape)))
+        y = y.contiguous()
+        K = y.shape[1]
+        miss = self.has_missing
+        b = self._buffers("tdot", st.n, st.p, K, False, miss)
+        sp = _capi.stream_ptr()
+        w = torch.empty((st.p, K), dtype=F64, device=st.device)
+        if m == 0:
+            w.zero_()
+        else:
+            _capi.check(lib.lmdec_colabsmax(_capi.ptr(y), K, m, K, None, None, _capi.ptr(b["amax"]), None, sp))
+            mult = self._mult(b, False)
+            _capi.check(lib.lmdec_quantize_planes(_capi.ptr(y), K, st.n, m, K, self.planes, b["N"], _capi.ptr(mult),
+                                                  None, None, _capi.ptr(b["im1"]), None, sp), "quantize")
+            _capi.check(lib.lmdec_geno_matmul(_capi.ptr(st.v_store), st.p, st.n, st.p, m, int(miss), 1 if miss else 0,
+                                              _capi.ptr(b["im1"]), None, K, self.planes, b["N"],
+                                              _capi.ptr(b["out0"]), _capi.ptr(b["out1"]) if miss else None, 0, sp),
+                        "geno_matmul (A.T.dot)")
+            colscale = 1.0 / mult
+            d, mu = self.inv_std, self.impute_mean
+            rowshift = colshift = None
+            if self.mean is not None:
+                rowshift = -(self.mean if d is None else self.mean * d)
+                colshift = y.sum(0)
+            _capi.check(lib.lmdec_finalize(_capi.ptr(b["out0"]), _capi.ptr(b["out1"]) if miss else None, st.p, K,
+                                           _capi.ptr(colscale), _capi.ptr(mu) if miss else None, _capi.ptr(d),
+                                           _capi.ptr(rowshift), _capi.ptr(colshift), _capi.ptr(w), K, sp), "finalize")
+        if st.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(w, group=st.group)
+        return w[:, 0] if squeeze else w
+
+    # ------------------------------------------------------------------ materialisation (tests / small inputs)
+    def to_dense(self) -> torch.Tensor:
+        g = self.store.to_dense(rows=self.rows).to(F64)
+        if self.has_missing:
+            g = torch.where(g < 0, self.impute_mean.expand_as(g), g)
+        if self.mean is not None:
+            g = g - self.mean
+        if self.inv_std is not None:
+            g = g * self.inv_std
+        return g
+
+    def compute(self):
+        return self.to_dense().cpu().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.compute()
+        return a.astype(dtype) if dtype is not None else a
+
+
+class _Transposed:
+    def __init__(self, op: GenotypeOperator):
+        self.op = op
+
+    ndim = 2
+
+    @property
+    def shape(self):
+        return self.op.shape[::-1]
+
+    @property
+    def T(self):
+        return self.op
+
+    def dot(self, y):
+        return DeviceArray(self.op.tdot_t(as_tensor(y, self.op.store.device)))
+
+    def dot_t(self, y):
+        return self.op.tdot_t(y)
+
+    def tdot_t(self, t):
+        return self.op.dot_t(t)
+
+    def compute(self):
+        return self.op.compute().T
+
+    def __array__(self, dtype=None, copy=None):
+        return self.op.__array__(dtype).T
