@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the decomposition hot path (BASELINE.json): one power-iteration step  x <- A (A^T orth(x)) / n.
+
+  python bench.py --gpus N --steps K --warmup W            this build (CUDA, one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N ...            the reference's CPU path (NumPy oracle port, host cores)
+
+Workload at every N: BASELINE.json configs[1] per GPU -- a 1000G-shaped 2,504 x 1,000,000 genotype shard with 5 % iid
+missing (mean-imputed), centre + binomial scale, k = 10 (+ buffer 10 => K = 20).  At N > 1 the samples are row-sharded
+(global matrix (N*2504) x 1M, weak scaling) and the only collectives are the p x K all-reduce of A^T q and the K x K
+Gram all-reduce (NCCL).
+
+A "step" is one full iteration of PowerMethod.svd's loop body (accuracy: CholeskyQR2 + K x K SVD + q-vals; step:
+A^T q, A t) on data resident in HBM.  `value` = 4 n p K flops per step / time.  `e2e` runs the same Gram-operator
+application through the public operator API with HOST operands: q (pinned host) -> H2D -> A.T.dot -> A.dot -> D2H.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS, N_COLS, K_TOP, BUFFER, MISS = 2504, 1_000_000, 10, 10, 0.05
+METRIC = "A^T.A.Q throughput of one power-iteration step (TFLOP/s; 4npK flop per step)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tensor_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "tensor_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the NumPy oracle (port of the reference's dask path) on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_step_throughput(steps: int, warmup: int, budget_s: float = 25.0):
+    """Times oracle PowerMethod._solution_step on a column sample of the workload (same n, K, missing rate)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lmdec_oracle as oracle
+
+    def synth_genotypes(n, p, miss, seed, dtype):
+        rng = np.random.default_rng(seed)
+        maf = rng.uniform(0.05, 0.5, size=p)
+        g = np.random.default_rng(seed + 1).binomial(2, maf, size=(n, p)).astype(dtype)
+        g[np.random.default_rng(seed + 2).random((n, p)) < miss] = np.nan
+        return g
+
+    cores = os.cpu_count() or 1
+    p_s = 40_000
+    g = synth_genotypes(N_ROWS, p_s, MISS, seed=0, dtype=np.float32)
+    op = oracle.make_snp_array(g, std_method="binom")
+    pm = oracle.PowerMethod(k=K_TOP, buffer=BUFFER, sub_svd_start=False, lmbd=0)
+    x = pm._initialization(op, x0=np.random.default_rng(42).standard_normal((N_ROWS, K_TOP + BUFFER)))
+    times = []
+    t_begin = time.time()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        x = pm._solution_step(x)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.time() - t_begin > budget_s and len(times) >= 1:
+            break
+    t = float(np.mean(times))
+    flops = 4.0 * N_ROWS * p_s * (K_TOP + BUFFER)
+    return {"value": flops / t / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+            "sample": f"oracle PowerMethod._solution_step on a {N_ROWS}x{p_s} column sample of the workload "
+                      f"({len(times)} steps, {t * 1e3:.1f} ms/step, threaded BLAS, float64)",
+            "ms_per_step": t * 1e3, "steps": len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_step_throughput(args.steps, args.warmup, budget_s=120.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": f"configs[1]: 1000G-shaped {N_ROWS}x{N_COLS} 2-bit genotypes per GPU, 5% missing "
+                        f"(mean-impute), center+binom scale, PowerMethod k={K_TOP} buffer={BUFFER} (K=20), "
+                        f"3 int8 planes (22-bit fixed point)",
+            "global_shape": [N_ROWS * n_gpus, N_COLS], "K": K_TOP + BUFFER,
+            "parallelism": f"row-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
+            "l2": "inputs larger than L2 (2 x 626 MB tile stores per step vs 126 MB L2)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# this build
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_shard(torch, device, n, p, miss, seed):
+    """synthetic genotypes generated on the device in row blocks (never a dense float matrix in HBM)."""
+    from lmdec_b200.store import GenotypeStore
+    gen = torch.Generator(device=device).manual_seed(seed)
+    maf = torch.rand(p, generator=torch.Generator(device=device).manual_seed(0), device=device) * 0.45 + 0.05
+    store = GenotypeStore(n, p, device=device)
+    for r0 in range(0, n, 256):
+        nb = min(256, n - r0)
+        g = (torch.rand((nb, p), generator=gen, device=device) < maf).to(torch.int8)
+        g += (torch.rand((nb, p), generator=gen, device=device) < maf).to(torch.int8)
+        if miss:
+            g[torch.rand((nb, p), generator=gen, device=device) < miss] = -1
+        store.pack_rows(g, r0)
+    store.finish()
+    return store
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from lmdec_b200 import PowerMethod, _capi
+    from lmdec_b200 import store as store_mod
+    from lmdec_b200.store import GenotypeOperator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path is the only path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
+    lib = _capi.load()
+    K = K_TOP + BUFFER
+    n_global = N_ROWS * world
+
+    t0 = time.time()
+    store = make_shard(torch, device, N_ROWS, N_COLS, MISS, seed=1000 + rank)
+    store.group, store.n_global, store.row_offset = group, n_global, rank * N_ROWS
+    mean, std = store.moments("binom")
+    op = GenotypeOperator(store, mean, 1.0 / std, planes=args.planes)
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+
+    pm = PowerMethod(k=K_TOP, buffer=BUFFER, tol=1e-30, scoring_method="q-vals", sub_svd_start=False, lmbd=0,
+                     max_iter=10 ** 6)
+    pm._reset_history()
+    x0_full = np.random.default_rng(42).standard_normal((n_global, K))
+    x = pm._initialization(op, x0=x0_full[rank * N_ROWS:(rank + 1) * N_ROWS])
+
+    def one_step(x):
+        pm._solution_accuracy(x)
+        return pm._solution_step(x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        x = one_step(x)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    store_mod.KERNEL_EVENTS = []
+    launches0 = lib.lmdec_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        x = one_step(x)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.lmdec_launch_count() - launches0
+    kernel_events = store_mod.KERNEL_EVENTS
+    store_mod.KERNEL_EVENTS = None
+    k_ms = {"dot": [], "tdot": []}
+    for tag, a, b in kernel_events:
+        k_ms[tag].append(a.elapsed_time(b))
+
+    # ---- e2e: public operator API with host operands (pinned), H2D + D2H inside the timed region
+    q_host = torch.from_numpy(np.linalg.qr(x0_full[rank * N_ROWS:(rank + 1) * N_ROWS])[0]).pin_memory()
+    out_host = torch.empty((N_ROWS, K), dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        qd = q_host.to(device, non_blocking=True)
+        xd = op.dot(op.T.dot(qd))
+        out_host.copy_(xd.t, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    sampler.stop_flag = True
+    e2e_ms_total = f0.elapsed_time(f1)
+
+    times = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_step = float(times[0].item()) / args.steps
+    e2e_ms_step = float(times[1].item()) / args.steps
+    flops_step = 4.0 * n_global * N_COLS * K
+
+    # ---- time-to-converged SVD through PowerMethod.svd (informative; BASELINE metric's first half)
+    svd_info = None
+    if rank == 0 or world > 1:
+        pm2 = PowerMethod(k=K_TOP, buffer=BUFFER, tol=1e-4, scoring_method="q-vals", sub_svd_start=False, lmbd=0,
+                          max_iter=100)
+        barrier()
+        ts = time.time()
+        pm2.svd(op, x0=x0_full[rank * N_ROWS:(rank + 1) * N_ROWS], verbose=False)
+        torch.cuda.synchronize()
+        svd_info = {"seconds": time.time() - ts, "iterations": pm2.num_iter, "tol": 1e-4,
+                    "store_build_seconds": t_build}
+
+    if rank == 0:
+        pk = peaks()
+        n_launch = len(k_ms["dot"]) + len(k_ms["tdot"])
+        avg_kernel_ms = (sum(k_ms["dot"]) + sum(k_ms["tdot"])) / max(n_launch, 1)
+        flops_launch = 2.0 * N_ROWS * N_COLS * K          # per GPU, per geno_mma launch (one of the two products)
+        achieved = flops_launch / (avg_kernel_ms * 1e-3) / 1e12
+        t_tensor = flops_launch / (pk["tensor_tflops"] * 1e12)
+        t_hbm = (N_ROWS * N_COLS / 4) / (pk["hbm_gbs"] * 1e9)
+        line = {
+            "metric": METRIC, "value": flops_step / (ms_step * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int8 x int8 -> int32 tensor cores (exact), f64 small algebra",
+            "data": "synthetic", "config": workload_config(world),
+            "clocks": sampler.summary(),
+            "e2e": {"value": flops_step / (e2e_ms_step * 1e-3) / 1e12, "unit": "TFLOP/s",
+                    "h2d_bytes_per_step": N_ROWS * K * 8, "d2h_bytes_per_step": N_ROWS * K * 8,
+                    "ms_per_step": e2e_ms_step,
+                    "api": "x = op.dot(op.T.dot(q)) with q, x in pinned host memory (GenotypeOperator from make_snp_array)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tensor_tflops"], "traffic": None,
+                         "kernel": "geno_mma_kernel (2 launches per step: A^T q and A t)",
+                         "avg_launch_ms": avg_kernel_ms, "dot_ms": float(np.mean(k_ms["dot"])) if k_ms["dot"] else None,
+                         "tdot_ms": float(np.mean(k_ms["tdot"])) if k_ms["tdot"] else None,
+                         "kernel_share_of_step": (sum(k_ms["dot"]) + sum(k_ms["tdot"])) / ms_total,
+                         "algorithmic_flops_per_launch": flops_launch,
+                         "algorithmic_bytes_per_launch": N_ROWS * N_COLS / 4,
+                         "t_tensor_ms": t_tensor * 1e3, "t_hbm_ms": t_hbm * 1e3, "peak_source": pk["source"]},
+            "svd": svd_info,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = {k: v for k, v in cpu_step_throughput(3, 1).items()
+                                    if k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--planes", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,8 +13,8 @@
  *   - no global state: thread-compatible (one stream per caller).
  *
  * Genotype store ("tile store"): 2-bit dosage codes, 4 per byte, LSB first: 0,1,2 = dosage, 3 = missing (NaN).
- * A PLINK .bed byte (00 hom-A1, 01 missing, 10 het, 11 hom-A2; pandas_plink reads these as 0,NaN,1,2) maps to a
- * store byte with  c' = (c >> 1) + ((c & 1) ? ((c >> 1) ? 1 : 3) : 0)  per 2-bit field; see lmdec_recode_bed.
+ * A PLINK .bed 2-bit field (hi lo): 00 hom-A1, 01 missing, 10 het, 11 hom-A2 (pandas_plink reads these as 0, NaN, 1, 2)
+ * maps to the store code (hi' lo') = (lo, lo ^ hi); see lmdec_recode_bed.
  * A store holds a logical  M x Kd  matrix (M = output rows of a product, Kd = the contraction axis) as
  *   tile(mp, kc) = 8192 bytes for rows [128*mp, +128) x contraction [256*kc, +256), tiles ordered mp-major;
  *   inside a tile: byte (t, b) of row t's 64 packed bytes sits at  (b/16)*2048 + t*16 + b%16
@@ -37,6 +37,8 @@ enum lmdec_dtype { LMDEC_I8 = 0, LMDEC_U8 = 1, LMDEC_F32 = 2, LMDEC_F64 = 3 };
 
 const char* lmdec_last_error(void);
 int lmdec_abi_version(void);
+/* number of CUDA kernels this library has launched in the process (bench.py reports the delta per timed region) */
+long long lmdec_launch_count(void);
 
 /* bytes of a tile store holding a logical M x Kd matrix */
 int64_t lmdec_store_bytes(int64_t M, int64_t Kd);
@@ -112,7 +114,7 @@ int lmdec_gram(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64
 int lmdec_qvals(const double* si, const double* sj, int k, int scale, double* out, void* stream);
 /* rmse_k's Frobenius part (metrics.py:161): out[0] = sum_{m,k} (A[m,k] - B[m,k]*s[k])^2  (deterministic). */
 int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, const double* s, int64_t m, int K,
-                 double* out, double* work, void* stream);
+                 double* out, double* work /* >= 592 doubles */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ _i64, _i32, _p = C.c_int64, C.c_int, C.c_void_p
 SIGNATURES = {
     "lmdec_last_error": (C.c_char_p, []),
     "lmdec_abi_version": (_i32, []),
+    "lmdec_launch_count": (C.c_longlong, []),
     "lmdec_store_bytes": (_i64, [_i64, _i64]),
     "lmdec_image_bytes": (_i64, [_i64, _i32]),
     "lmdec_pack_2bit": (_i32, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i64, _i64, _p, _p]),

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <atomic>
 #include "../../include/lmdec_b200.h"
 #include "geno_mma.cuh"
 
@@ -13,7 +14,9 @@ int fail(const char* fmt, const char* a = "") {
   snprintf(g_err, sizeof(g_err), fmt, a);
   return 1;
 }
-int check_launch(const char* what) {
+std::atomic<long long> g_launches{0};
+int check_launch(const char* what, int n_kernels = 1) {
+  g_launches.fetch_add(n_kernels, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -397,6 +400,7 @@ extern "C" {
 
 const char* lmdec_last_error(void) { return g_err; }
 int lmdec_abi_version(void) { return 1; }
+long long lmdec_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int64_t lmdec_store_bytes(int64_t M, int64_t Kd) { return cdiv(M, 128) * cdiv(Kd, 256) * 8192; }
 int64_t lmdec_image_bytes(int64_t Kd, int N) { return cdiv(Kd, 256) * 8 * (int64_t)N * 32; }
@@ -581,7 +585,7 @@ int lmdec_gram(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64
   }
   gram_partial_kernel<<<nb, 256, smem, st>>>(X, ldx, Y, ldy, m, K, work);
   gram_final_kernel<<<(unsigned)cdiv(K * K + K, 128), 128, 0, st>>>(work, nb, K, G, colsum);
-  return check_launch("lmdec_gram");
+  return check_launch("lmdec_gram", 2);
 }
 
 int lmdec_qvals(const double* si, const double* sj, int k, int scale, double* out, void* stream) {
@@ -597,7 +601,7 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
   cudaStream_t st = (cudaStream_t)stream;
   sqdiff_partial_kernel<<<(unsigned)nb, 256, 0, st>>>(A, lda, B, ldb_, s, m, K, work);
   sum_final_kernel<<<1, 32, 0, st>>>(work, (int)nb, out);
-  return check_launch("lmdec_sqdiff");
+  return check_launch("lmdec_sqdiff", 2);
 }
 
 }  // extern "C"

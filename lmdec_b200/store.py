@@ -29,6 +29,26 @@ from .device import F64, DeviceArray, as_tensor, require_cuda
 _DTYPE_CODE = {torch.int8: 0, torch.uint8: 1, torch.float32: 2, torch.float64: 3}
 
 
+# bench.py sets this to a list to time the dominant kernel with CUDA events on the launching stream
+KERNEL_EVENTS = None
+
+
+class _timed:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if KERNEL_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if KERNEL_EVENTS is not None:
+            self.e1.record()
+            KERNEL_EVENTS.append((self.tag, self.e0, self.e1))
+
+
 def _round16(x: int) -> int:
     return (x + 15) // 16 * 16
 
@@ -300,9 +320,11 @@ class GenotypeOperator:
         x = torch.empty((m, K), dtype=F64, device=st.device)
         if m == 0:
             return x[:, 0] if squeeze else x
-        _capi.check(lib.lmdec_geno_matmul(_capi.ptr(st.s_store), st.n, st.p, m, st.p, int(miss), 0,
-                                          _capi.ptr(b["im1"]), _capi.ptr(b["im2"]) if miss else None, K, self.planes,
-                                          b["N"], _capi.ptr(b["out0"]), None, 0, sp), "geno_matmul (A.dot)")
+        with _timed("dot"):
+            _capi.check(lib.lmdec_geno_matmul(_capi.ptr(st.s_store), st.n, st.p, m, st.p, int(miss), 0,
+                                              _capi.ptr(b["im1"]), _capi.ptr(b["im2"]) if miss else None, K,
+                                              self.planes, b["N"], _capi.ptr(b["out0"]), None, 0, sp),
+                        "geno_matmul (A.dot)")
         colscale = 1.0 / mult
         colshift = None
         if self.mean is not None:
@@ -334,10 +356,11 @@ class GenotypeOperator:
             mult = self._mult(b, False)
             _capi.check(lib.lmdec_quantize_planes(_capi.ptr(y), K, st.n, m, K, self.planes, b["N"], _capi.ptr(mult),
                                                   None, None, _capi.ptr(b["im1"]), None, sp), "quantize")
-            _capi.check(lib.lmdec_geno_matmul(_capi.ptr(st.v_store), st.p, st.n, st.p, m, int(miss), 1 if miss else 0,
-                                              _capi.ptr(b["im1"]), None, K, self.planes, b["N"],
-                                              _capi.ptr(b["out0"]), _capi.ptr(b["out1"]) if miss else None, 0, sp),
-                        "geno_matmul (A.T.dot)")
+            with _timed("tdot"):
+                _capi.check(lib.lmdec_geno_matmul(_capi.ptr(st.v_store), st.p, st.n, st.p, m, int(miss),
+                                                  1 if miss else 0, _capi.ptr(b["im1"]), None, K, self.planes, b["N"],
+                                                  _capi.ptr(b["out0"]), _capi.ptr(b["out1"]) if miss else None, 0, sp),
+                            "geno_matmul (A.T.dot)")
             colscale = 1.0 / mult
             d, mu = self.inv_std, self.impute_mean
             rowshift = colshift = None
