@@ -21,34 +21,41 @@ def _allreduce(t: torch.Tensor, group):
     return t
 
 
-def _whiten_factor(G: np.ndarray):
-    """Return (r_inv, r) with r_inv^T G r_inv = I.  Cholesky when G is numerically SPD, eigen-decomposition otherwise."""
+def _whiten_factor(G: np.ndarray, rank_tol: float = 1e-12):
+    """Return (r_inv, r, deficient) with r_inv^T G r_inv = I on the numerical range of G.
+
+    G is first scaled to unit diagonal (column scales of the iterate can differ by many orders of magnitude), then
+    factored by Cholesky; a pivot below `rank_tol` switches to an eigen-decomposition that drops the null directions
+    (their columns of r_inv are zero and `deficient` is True)."""
     if not np.all(np.isfinite(G)):
         # what LAPACK reports through dask/numpy when NaN/Inf reach the QR: tests/test_iter_methods.py:318-325
         raise np.linalg.LinAlgError("SVD did not converge (non-finite values in the iterate)")
     K = G.shape[0]
     G = (G + G.T) / 2
+    d = np.sqrt(np.clip(np.diag(G), 0, None))
+    zero = d == 0
+    d_safe = np.where(zero, 1.0, d)
+    Gs = G / np.outer(d_safe, d_safe)
     try:
-        dmax = float(np.max(np.diag(G)))
-        if dmax <= 0 or np.min(np.diag(G)) <= dmax * 1e-28:
-            raise np.linalg.LinAlgError("degenerate column")
-        L = np.linalg.cholesky(G)
-        r = L.T
-        r_inv = np.linalg.solve(r, np.eye(K))
-        if not np.all(np.isfinite(r_inv)):
-            raise np.linalg.LinAlgError("singular")
-        return r_inv, r, False
+        if zero.any():
+            raise np.linalg.LinAlgError("zero column")
+        L = np.linalg.cholesky(Gs)
+        if np.min(np.diag(L)) ** 2 < rank_tol:
+            raise np.linalg.LinAlgError("numerically rank deficient")
+        rs = L.T
+        rs_inv = np.linalg.solve(rs, np.eye(K))
+        deficient = False
     except np.linalg.LinAlgError:
-        lam, V = np.linalg.eigh(G)
-        lam_max = max(float(lam[-1]), 0.0)
-        keep = lam > lam_max * 1e-24 if lam_max > 0 else np.zeros(K, dtype=bool)
+        lam, V = np.linalg.eigh(Gs)
+        keep = lam > rank_tol
         inv_sqrt = np.where(keep, 1.0 / np.sqrt(np.where(keep, lam, 1.0)), 0.0)
-        r_inv = V * inv_sqrt
-        r = (V * np.sqrt(np.clip(lam, 0, None))).T
-        return r_inv, r, not bool(np.all(keep))
+        rs_inv = V * inv_sqrt
+        rs = (V * np.sqrt(np.clip(lam, 0, None))).T
+        deficient = not bool(np.all(keep))
+    return rs_inv / d_safe[:, None], rs * d_safe[None, :], deficient
 
 
-def orthonormalize(x: torch.Tensor, group=None, seed: int = 0):
+def orthonormalize(x: torch.Tensor, group=None, seed: int = 0, gram_fn=None):
     """CholeskyQR2: returns (q [n,K] orthonormal, r [K,K] float64 on the host) with x = q r.
 
     Rank-deficient iterates (the reference's Householder QR completes them with arbitrary orthonormal columns) get
@@ -59,8 +66,9 @@ def orthonormalize(x: torch.Tensor, group=None, seed: int = 0):
     K = x.shape[1]
     r_total = np.eye(K)
     q = x
+    gram_fn = gram_fn or gram      # the device kernel; tests of the host logic pass a CPU stand-in
     for it in range(4):
-        G = _allreduce(gram(q), group).cpu().numpy()
+        G = _allreduce(gram_fn(q), group).cpu().numpy()
         if it >= 2 and np.max(np.abs(G - np.eye(K))) < 1e-9:
             break
         r_inv, r, deficient = _whiten_factor(G)

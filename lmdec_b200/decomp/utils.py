@@ -55,6 +55,37 @@ def mask_imputation(array, mask_values=None, fill_value=0, mask_method: str = "m
     return DeviceArray(filled), DeviceArray(mask)
 
 
+def _make_dense_snp_array(array, mean, std, std_method, mask_nan):
+    from ..array.chained import ChainedArray
+    from ..array.stacked import StackedArray
+    a = as_tensor(array)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D array")
+    nan = torch.isnan(a)
+    col_mean = torch.nanmean(a, dim=0)
+    if std:
+        if std_method == "binom":
+            u = col_mean / 2
+            col_std = torch.sqrt(2 * u * (1 - u))
+        elif std_method == "norm":
+            cnt = (~nan).sum(dim=0)
+            dev = torch.where(nan, torch.zeros_like(a), a - col_mean)
+            col_std = torch.sqrt((dev * dev).sum(dim=0) / cnt)
+        else:
+            raise NotImplementedError(f"std_method, {std_method}, is not implemented ")
+    if mask_nan and bool(nan.any().item()):
+        a = torch.where(nan, col_mean.expand_as(a), a)
+    out = a
+    if mean:
+        out = StackedArray((out, -col_mean))
+    if std:
+        out = ChainedArray((out, 1.0 / col_std))
+    if not mean and not std:
+        from ..array.operators import DenseOperator
+        out = DenseOperator(out)
+    return out
+
+
 def make_snp_array(array, mean: bool = True, std: bool = True, std_method: str = "binom", dtype="int8",
                    rechunk="auto", mask_method: str = "mean", mask_nan: bool = True, planes: int = 3,
                    device=None, group=None, n_global: Optional[int] = None, row_offset: int = 0) -> GenotypeOperator:
@@ -68,7 +99,13 @@ def make_snp_array(array, mean: bool = True, std: bool = True, std_method: str =
     if isinstance(array, GenotypeStore):
         store = array
     else:
-        store = GenotypeStore.from_dense(array, device=device, group=group, n_global=n_global, row_offset=row_offset)
+        try:
+            store = GenotypeStore.from_dense(array, device=device, group=group, n_global=n_global,
+                                             row_offset=row_offset)
+        except ValueError:
+            # not a genotype matrix (the reference's own tests feed random floats, tests/test_iter_methods.py:12-33):
+            # same operator over a dense device matrix, products are library GEMMs
+            return _make_dense_snp_array(array, mean, std, std_method, mask_nan)
     if store.has_missing and not mask_nan:
         raise ValueError("array holds NaN; the 2-bit store always mean-imputes them (mask_nan=True)")
     m, s = store.moments(std_method if std else "binom")
