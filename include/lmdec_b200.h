@@ -67,7 +67,7 @@ int lmdec_store_transpose(const uint8_t* src, int64_t M, int64_t Kd, uint8_t* ds
 int lmdec_code_counts(const uint8_t* store, int64_t M, int64_t Kd, int64_t kd_limit, int64_t* counts, void* stream);
 
 /* Quantise a float64 operand  B[kd, k] * row1[kd] (* row2[kd])  into P signed-byte planes laid out as the tensor-core
- * B image: image[kd/32][N*32] in the no-swizzle K-major core-matrix order, column n = plane*K + k,
+ * B image: image[kd/32][N*32] in the no-swizzle K-major core-matrix order, column n = k*P + plane,
  * value = round(B * mult[k]) written as balanced base-256 digits.  rows >= kd_limit and columns >= P*K are zero.
  * row1/row2 may be NULL.  image2 (optional) receives the planes of B*row1*row2 (the mean-imputation operand
  * mu o D T  of StackedArray.dot's sparse-mask term, lmdec/array/stacked.py:204-217).  */

@@ -6,27 +6,35 @@
 // Replaces the chunked int8->f64 matmuls under PowerMethod._solution_step (reference
 // lmdec/decomp/iter_methods.py:381-386 -> lmdec/array/stacked.py:172-217, chained.py:169-177).
 //
-// CTA = 11 warps, one CTA per SM, persistent over work items (m-tile, k-split):
-//   warps 0-7  producers: coalesced LDG of the packed tile (1 row per thread), 2-bit -> uint8 decode in registers,
-//              tcgen05.st straight into the TMEM A ring; afterwards the epilogue (TMEM -> smem -> int64 combine)
-//   warp  8    B loader: one thread, cp.async.bulk of the pre-laid-out plane image into a smem ring
-//   warps 9,10 MMA issuers: one thread each.  A narrow-N tcgen05.mma is limited by the issuing thread (~45-54 cycles
-//              per instruction, profiles/r01/umma_probe4_issuers.log); two issuers reach the N/2-cycle math rate.
-//              Without missing data they take alternate K-blocks; with missing data issuer 0 runs the value plane and
-//              issuer 1 the indicator plane.  Each owns one accumulator.
+// CTA = 16 warps, one CTA per SM, persistent over work items (m-tile, k-split).  Every role streams across work-item
+// boundaries, so HBM latency is paid once per launch, not once per tile:
+//   warps 0-7   producers: read their row of the packed tile from the smem ring (conflict-free 16-byte pieces), decode
+//               2-bit -> uint8 in registers, tcgen05.st straight into the TMEM A ring
+//   warp  8     tile loader: one thread, cp.async.bulk (TMA engine) of whole 8 KB store tiles into an 8-deep smem ring
+//   warp  15    B loader: one thread, cp.async.bulk of the pre-laid-out plane image into its own smem ring
+//   warps 9,10  MMA issuers: one thread each.  A narrow-N tcgen05.mma is limited by the issuing thread (~45-54 cycles
+//               per instruction, profiles/r01/umma_probe4_issuers.log); two issuers reach the N/2-cycle math rate.
+//               Without missing data they take alternate K-blocks; with missing data issuer 0 runs the value plane and
+//               issuer 1 the indicator plane.  Each owns one accumulator of the current accumulator set.
+//   warps 11-14 epilogue: TMEM -> registers -> exact int64 plane combine -> global (store or atomicAdd).
+//               With N <= 64 there are two accumulator sets, so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include "umma.cuh"
 
 namespace lmdec {
 
 constexpr int kProducerWarps = 8;
-constexpr int kLoaderWarp = 8;
+constexpr int kTileLoaderWarp = 8;
 constexpr int kIssuerWarp0 = 9;
-constexpr int kThreads = 11 * 32;
+constexpr int kEpilogueWarp0 = 11;
+constexpr int kEpilogueWarps = 4;
+constexpr int kBLoaderWarp = 15;
+constexpr int kThreads = 16 * 32;
 constexpr int kKbPerChunk = 8;             // 8 K-blocks of 32 = one 256-wide contraction chunk = one store tile
-constexpr uint32_t kAccCols = 128;         // accumulator i at TMEM column i*128
-constexpr uint32_t kARingCol0 = 256;       // A ring: columns [256, 512)
+constexpr uint32_t kARingCol0 = 256;       // TMEM A ring: columns [256, 512); accumulators: [0, 256)
 constexpr int kMaxBStages = 4;
+constexpr int kMaxTileStages = 8;
+constexpr uint32_t kTileBytes = 8192;
 
 struct GenoMmaParams {
   const uint8_t* store;
@@ -44,34 +52,24 @@ struct GenoMmaParams {
   long long* out0;
   long long* out1;
   int b_stages;
+  int tile_stages;
   int use_atomics;
 };
-
-__device__ __forceinline__ uint4 ldg_stream16(const uint8_t* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
-  return v;
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // 16 codes in r -> 4 words of 4 uint8 each; word k holds codes k, k+4, k+8, k+12 (the B image is permuted to match)
 template <bool kMiss>
 __device__ __forceinline__ void decode16(uint32_t r, uint32_t* v, uint32_t* m) {
+  if (kMiss) {
+    const uint32_t t = r & (r >> 1) & 0x55555555u;  // bit 2i set where code i == 3 (missing)
+    const uint32_t rv = r ^ (t * 3u);               // missing -> dosage 0
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t x = (r >> (2 * k)) & 0x03030303u;
-    if (kMiss) {
-      const uint32_t both = x & (x >> 1) & 0x01010101u;  // code 3 = missing
-      v[k] = x ^ (both * 3u);
-      m[k] = both;
-    } else {
-      v[k] = x;
+    for (int k = 0; k < 4; ++k) {
+      v[k] = (rv >> (2 * k)) & 0x03030303u;
+      m[k] = (t >> (2 * k)) & 0x01010101u;
     }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (r >> (2 * k)) & 0x03030303u;
   }
 }
 
@@ -93,22 +91,95 @@ __device__ __forceinline__ void produce_chunk(const uint4 (&raw)[2], uint32_t a_
   }
 }
 
+// Epilogue of one warp (one TMEM lane quarter, thread = output row).  Accumulator column n = k*P + plane, so the P
+// planes of 8 consecutive outputs are 8*P consecutive columns: everything stays in registers, indices are compile-time.
+template <int P>
+__device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t tbase, uint64_t* acc_full,
+                                              uint64_t* acc_empty, int warp, int lane, int acc_sets, uint32_t acc_w) {
+  const int q = warp & 3;  // TMEM lane quarter this warp may touch
+  const int row = q * 32 + lane;
+  const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
+  const int K = p.K;
+  const int n_groups = (K + 7) / 8;
+  const int n_work = p.m_tiles * p.splits;
+  const int n_pass = (p.mode == 1) ? 2 : 1;
+  uint32_t tile_no = 0;
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
+    const int mt = w % p.m_tiles;
+    const uint32_t set = tile_no % acc_sets, set_phase = (tile_no / acc_sets) & 1;
+    const uint32_t acc0 = lane_addr + (set * 2) * acc_w, acc1 = acc0 + acc_w;
+    mbar_wait(&acc_full[set], set_phase);
+    tc_fence_after_sync();
+    const long long m = (long long)mt * 128 + row;
+    const bool live = m < p.m_limit;
+    for (int pass = 0; pass < n_pass; ++pass) {
+      long long* dst = (pass == 0 ? p.out0 : p.out1) + m * K;
+      for (int g = 0; g < n_groups; ++g) {
+        uint32_t r[8 * P];
+        const uint32_t col = (uint32_t)g * 8 * P;
+#pragma unroll
+        for (int i = 0; i < P; ++i) tmem_ld8p((p.mode == 1 && pass == 1 ? acc1 : acc0) + col + i * 8, r + 8 * i);
+        if (p.mode == 0) {
+          uint32_t r1[8 * P];
+#pragma unroll
+          for (int i = 0; i < P; ++i) tmem_ld8p(acc1 + col + i * 8, r1 + 8 * i);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8 * P; ++i) r[i] += r1[i];
+        } else {
+          tmem_wait_ld();
+        }
+        if (g == n_groups - 1 && pass == n_pass - 1) {
+          // all TMEM reads of this tile are done: hand the accumulator set back to the issuers
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[set]);
+        }
+        if (live) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const int k = g * 8 + kk;
+            if (k < K) {
+              long long acc = (long long)(int)r[kk * P + P - 1];
+#pragma unroll
+              for (int pl = P - 2; pl >= 0; --pl) acc = acc * 256 + (long long)(int)r[kk * P + pl];
+              if (p.use_atomics)
+                atomicAdd(reinterpret_cast<unsigned long long*>(dst + k), (unsigned long long)acc);
+              else
+                dst[k] = acc;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full_a[4], empty_a[4], full_b[kMaxBStages], empty_b[kMaxBStages], acc_full, acc_empty;
+  __shared__ uint64_t full_t[kMaxTileStages], empty_t[kMaxTileStages];  // packed tiles (smem ring)
+  __shared__ uint64_t full_a[4], empty_a[4];                            // decoded A (TMEM ring)
+  __shared__ uint64_t full_b[kMaxBStages], empty_b[kMaxBStages];        // B image (smem ring)
+  __shared__ uint64_t acc_full[2], acc_empty[2];                        // accumulator sets
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N;
   const uint32_t img_bytes = (uint32_t)kKbPerChunk * N * 32;
   const uint32_t stage_bytes = img_bytes * p.n_img;
-  uint8_t* smem_b = smem;
-  int* stage_out = reinterpret_cast<int*>(smem + (size_t)p.b_stages * stage_bytes);  // [128][N+1] int32
+  uint8_t* smem_t = smem;                                              // tile ring
+  uint8_t* smem_b = smem + (size_t)p.tile_stages * kTileBytes;         // B ring
   const int a_stages = p.has_missing ? 2 : 4;
   const uint32_t a_stage_cols = p.has_missing ? 128 : 64;
+  const int acc_sets = N <= 64 ? 2 : 1;
+  const uint32_t acc_w = N <= 64 ? 64 : 128;
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 32) {
+    for (int i = 0; i < kMaxTileStages; ++i) {
+      mbar_init(&full_t[i], 1);
+      mbar_init(&empty_t[i], kProducerWarps);
+    }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&full_a[i], kProducerWarps);
       mbar_init(&empty_a[i], 2);
@@ -117,8 +188,10 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       mbar_init(&full_b[i], 1);
       mbar_init(&empty_b[i], 2);
     }
-    mbar_init(&acc_full, 2);
-    mbar_init(&acc_empty, kProducerWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 2);
+      mbar_init(&acc_empty[i], kEpilogueWarps);
+    }
     mbar_fence_init();
   }
   tc_fence_before_sync();
@@ -130,26 +203,22 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   const int chunks_per_split = (p.n_chunks + p.splits - 1) / p.splits;
 
   if (warp < kProducerWarps) {
-    // ------------------------------------------------------------------ producers + epilogue
+    // ------------------------------------------------------------------ producers
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
-    uint32_t a_stage = 0, a_phase = 0, acc_phase = 0;
+    const uint32_t my_off = (uint32_t)(2 * half) * 2048 + (uint32_t)row * 16;
+    uint32_t a_stage = 0, a_phase = 0, t_stage = 0, t_phase = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int mt = w % p.m_tiles, sp = w / p.m_tiles;
+      const int sp = w / p.m_tiles;
       const int c0 = sp * chunks_per_split;
       const int c1 = min(c0 + chunks_per_split, p.n_chunks);
-      const uint8_t* tile0 = p.store + ((size_t)mt * p.store_kc) * 8192 + (size_t)(2 * half) * 2048 + (size_t)row * 16;
-      uint4 raw[2], nxt[2];
-      if (c0 < c1) {
-        raw[0] = ldg_stream16(tile0 + (size_t)c0 * 8192);
-        raw[1] = ldg_stream16(tile0 + (size_t)c0 * 8192 + 2048);
-      }
       for (int c = c0; c < c1; ++c) {
-        if (c + 1 < c1) {
-          nxt[0] = ldg_stream16(tile0 + (size_t)(c + 1) * 8192);
-          nxt[1] = ldg_stream16(tile0 + (size_t)(c + 1) * 8192 + 2048);
-        }
+        mbar_wait(&full_t[t_stage], t_phase);
+        const uint8_t* src = smem_t + (size_t)t_stage * kTileBytes + my_off;
+        uint4 raw[2];
+        raw[0] = *reinterpret_cast<const uint4*>(src);
+        raw[1] = *reinterpret_cast<const uint4*>(src + 2048);
         mbar_wait(&empty_a[a_stage], a_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t a_addr = lane_addr + kARingCol0 + a_stage * a_stage_cols;
@@ -160,63 +229,42 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
         tmem_wait_st();
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full_a[a_stage]);
+        if (lane == 0) {
+          mbar_arrive(&full_a[a_stage]);
+          mbar_arrive(&empty_t[t_stage]);  // raw[] is consumed: the tile slot can be refilled
+        }
         if (++a_stage == (uint32_t)a_stages) {
           a_stage = 0;
           a_phase ^= 1;
         }
-        raw[0] = nxt[0];
-        raw[1] = nxt[1];
-      }
-      // ---- epilogue: TMEM -> smem staging -> exact int64 plane combine -> global
-      mbar_wait(&acc_full, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after_sync();
-      const int ld_s = N + 1;
-      const int n_pass = (p.mode == 1) ? 2 : 1;
-      for (int pass = 0; pass < n_pass; ++pass) {
-        // columns [half*N/2, (half+1)*N/2) of this lane quarter, 8 at a time (N is a multiple of 16)
-        for (int cb = half * (N / 2); cb < (half + 1) * (N / 2); cb += 8) {
-          uint32_t r0[8], r1[8];
-          if (p.mode == 1) {
-            tmem_ld8(lane_addr + pass * kAccCols + cb, r0);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) stage_out[row * ld_s + cb + i] = (int)r0[i];
-          } else {
-            tmem_ld8(lane_addr + cb, r0);
-            tmem_ld8(lane_addr + kAccCols + cb, r1);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) stage_out[row * ld_s + cb + i] = (int)r0[i] + (int)r1[i];
-          }
+        if (++t_stage == (uint32_t)p.tile_stages) {
+          t_stage = 0;
+          t_phase ^= 1;
         }
-        if (pass == n_pass - 1) {
-          // all TMEM reads of this tile are done: hand the accumulators back to the issuers
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty);
-        }
-        named_bar_sync(1, kProducerWarps * 32);
-        long long* out = pass == 0 ? p.out0 : p.out1;
-        const int K = p.K, P = p.P;
-        const long long m0 = (long long)mt * 128;
-        for (int idx = tid; idx < 128 * K; idx += kProducerWarps * 32) {
-          const int r = idx / K, k = idx - r * K;
-          if (m0 + r < p.m_limit) {
-            long long acc = 0;
-            for (int pl = P - 1; pl >= 0; --pl) acc = acc * 256 + (long long)stage_out[r * ld_s + pl * K + k];
-            long long* dst = out + (m0 + r) * K + k;
-            if (p.use_atomics)
-              atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)acc);
-            else
-              *dst = acc;
-          }
-        }
-        named_bar_sync(1, kProducerWarps * 32);
       }
     }
-  } else if (warp == kLoaderWarp) {
+  } else if (warp == kTileLoaderWarp) {
+    // ------------------------------------------------------------------ packed-tile loader (TMA bulk copies)
+    if (lane == 0) {
+      uint32_t t_stage = 0, t_phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int mt = w % p.m_tiles, sp = w / p.m_tiles;
+        const int c0 = sp * chunks_per_split;
+        const int c1 = min(c0 + chunks_per_split, p.n_chunks);
+        const uint8_t* tile0 = p.store + ((size_t)mt * p.store_kc) * kTileBytes;
+        for (int c = c0; c < c1; ++c) {
+          mbar_wait(&empty_t[t_stage], t_phase ^ 1);
+          mbar_arrive_expect_tx(&full_t[t_stage], kTileBytes);
+          bulk_g2s(smem_t + (size_t)t_stage * kTileBytes, tile0 + (size_t)c * kTileBytes, kTileBytes,
+                   &full_t[t_stage]);
+          if (++t_stage == (uint32_t)p.tile_stages) {
+            t_stage = 0;
+            t_phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == kBLoaderWarp) {
     // ------------------------------------------------------------------ B image loader
     if (lane == 0) {
       uint32_t b_stage = 0, b_phase = 0;
@@ -237,22 +285,25 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
         }
       }
     }
-  } else {
+  } else if (warp == kIssuerWarp0 || warp == kIssuerWarp0 + 1) {
     // ------------------------------------------------------------------ MMA issuers
     if (lane == 0) {
       const int me = warp - kIssuerWarp0;
       const uint32_t idesc = make_idesc_i8(128, (uint32_t)N, 0, 1);
       const uint32_t lbo = (uint32_t)N * 16;
-      const uint32_t d_addr = tbase + me * kAccCols;
       const uint32_t plane = p.has_missing ? (uint32_t)me : 0u;
       const uint32_t img = (p.has_missing && p.n_img == 2) ? (uint32_t)me : 0u;
-      uint32_t a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, acc_phase = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      // descriptor of the B ring base; stage / image / K-block offsets are added to its 16-byte address field
+      const uint64_t bdesc_ring = make_smem_desc(smem_u32(smem_b), lbo, 128);
+      uint32_t a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
+      uint32_t tile_no = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
         const int sp = w / p.m_tiles;
         const int c0 = sp * chunks_per_split;
         const int c1 = min(c0 + chunks_per_split, p.n_chunks);
-        mbar_wait(&acc_empty, acc_phase ^ 1);
-        acc_phase ^= 1;
+        const uint32_t set = tile_no % acc_sets, set_phase = (tile_no / acc_sets) & 1;
+        const uint32_t d_addr = tbase + (set * 2 + me) * acc_w;
+        mbar_wait(&acc_empty[set], set_phase ^ 1);
         tc_fence_after_sync();
         uint32_t accumulate = 0;
         for (int c = c0; c < c1; ++c) {
@@ -260,13 +311,20 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
           mbar_wait(&full_b[b_stage], b_phase);
           tc_fence_after_sync();
           const uint32_t a_addr = tbase + kARingCol0 + a_stage * a_stage_cols + plane * 64;
-          const uint32_t b_addr = smem_u32(smem_b + (size_t)b_stage * stage_bytes + (size_t)img * img_bytes);
+          const uint64_t bdesc0 = bdesc_ring + (uint64_t)((b_stage * stage_bytes + img * img_bytes) >> 4);
+          if (p.has_missing) {
 #pragma unroll
-          for (int j = 0; j < kKbPerChunk; ++j) {
-            if (!p.has_missing && (j & 1) != me) continue;
-            const uint64_t bdesc = make_smem_desc(b_addr + (uint32_t)j * N * 32, lbo, 128);
-            umma_ts_i8(d_addr, a_addr + j * 8, bdesc, idesc, accumulate);
-            accumulate = 1;
+            for (int j = 0; j < kKbPerChunk; ++j) {
+              umma_ts_i8(d_addr, a_addr + j * 8, bdesc0 + (uint64_t)(j * 2 * N), idesc, accumulate);
+              accumulate = 1;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < kKbPerChunk / 2; ++j) {
+              const int jj = 2 * j + me;
+              umma_ts_i8(d_addr, a_addr + jj * 8, bdesc0 + (uint64_t)(jj * 2 * N), idesc, accumulate);
+              accumulate = 1;
+            }
           }
           umma_commit(&empty_a[a_stage]);
           umma_commit(&empty_b[b_stage]);
@@ -279,11 +337,16 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
             b_phase ^= 1;
           }
         }
-        if (accumulate == 0) {
-          // (cannot happen: every work item has >= 1 chunk) keep the protocol alive anyway
-        }
-        umma_commit(&acc_full);
+        umma_commit(&acc_full[set]);
       }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 11..14)
+    switch (p.P) {
+      case 1: epilogue_loop<1>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w); break;
+      case 2: epilogue_loop<2>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w); break;
+      case 3: epilogue_loop<3>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w); break;
+      default: epilogue_loop<4>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w); break;
     }
   }
   tc_fence_before_sync();

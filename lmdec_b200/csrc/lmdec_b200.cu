@@ -223,7 +223,7 @@ __global__ void quantize_planes_kernel(const double* __restrict__ B, int64_t ldb
   const int64_t kb = kbh >> 1;
   uint32_t o1[4] = {0, 0, 0, 0}, o2[4] = {0, 0, 0, 0};
   if (n < K * P) {
-    const int pl = n / K, k = n - pl * K;
+    const int k = n / P, pl = n - k * P;  // column n = k*P + plane (geno_mma.cuh epilogue_loop)
     const double mk = mult[k];
     const double lim = ldexp(1.0, 8 * P - 2);
 #pragma unroll 4
@@ -518,30 +518,44 @@ int lmdec_geno_matmul(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_lim
   p.N = N;
   p.out0 = (long long*)out0;
   p.out1 = (long long*)out1;
-  // split-K: aim at >= 2 work items per SM, keep >= 4 chunks per split, cap the int32 accumulators (|acc| < 2^30)
+  // split-K: minimise the makespan  ceil(work / SMs) * (chunks per split + per-item overhead)  over the split count;
+  // the int32 accumulators cap a split at 8192 chunks (8192 * 256 * 2 * 127 < 2^30)
   int want = splits;
+  const int min_splits = (int)cdiv(p.n_chunks, 8192);
   if (want <= 0) {
-    want = 1;
-    if (p.m_tiles < 2 * n_sm) want = (int)cdiv(2 * n_sm, p.m_tiles);
-    const int max_by_len = p.n_chunks / 4 > 0 ? p.n_chunks / 4 : 1;
-    if (want > max_by_len) want = max_by_len;
+    const int max_s = p.n_chunks / 4 > 1 ? (p.n_chunks / 4 < 256 ? p.n_chunks / 4 : 256) : 1;
+    long long best = -1;
+    for (int s_ = min_splits > 1 ? min_splits : 1; s_ <= max_s; ++s_) {
+      const long long waves = cdiv((long long)p.m_tiles * s_, n_sm);
+      const long long cost = waves * (cdiv(p.n_chunks, s_) + 6) + (s_ > 1 ? 2 : 0);
+      if (best < 0 || cost < best) {
+        best = cost;
+        want = s_;
+      }
+    }
+    if (want <= 0) want = 1;
   }
-  const int min_splits = (int)cdiv(p.n_chunks, 8192);  // 8192 chunks * 256 * 2 * 128 = 2^29
   if (want < min_splits) want = min_splits;
   if (want > p.n_chunks) want = p.n_chunks;
   const int cps = (int)cdiv(p.n_chunks, want);
   p.splits = (int)cdiv(p.n_chunks, cps);
   p.use_atomics = p.splits > 1;
   const size_t stage_bytes = (size_t)8 * N * 32 * p.n_img;
-  const size_t staging = (size_t)128 * (N + 1) * 4;
-  int b_stages = (int)((200 * 1024 - staging) / stage_bytes);
+  const size_t scratch = 0;
+  const size_t budget = 225 * 1024;  // 227 KB per CTA minus static barriers and alignment slack
+  int tile_stages = kMaxTileStages, b_stages = 0;
+  for (; tile_stages >= 2; tile_stages /= 2) {
+    b_stages = (int)((budget - scratch - (size_t)tile_stages * kTileBytes) / stage_bytes);
+    if (b_stages >= 2) break;
+  }
   if (b_stages > kMaxBStages) b_stages = kMaxBStages;
-  if (b_stages < 2) return fail("lmdec_geno_matmul: shared memory budget");
+  if (b_stages < 2 || tile_stages < 2) return fail("lmdec_geno_matmul: shared memory budget");
   p.b_stages = b_stages;
-  const size_t smem = b_stages * stage_bytes + staging;
+  p.tile_stages = tile_stages;
+  const size_t smem = (size_t)tile_stages * kTileBytes + b_stages * stage_bytes + scratch;
   cudaStream_t st = (cudaStream_t)stream;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(geno_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(geno_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return fail("lmdec_geno_matmul: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
