@@ -69,8 +69,11 @@ int lmdec_code_counts(const uint8_t* store, int64_t M, int64_t Kd, int64_t kd_li
 /* Quantise a float64 operand  B[kd, k] * row1[kd] (* row2[kd])  into P signed-byte planes laid out as the tensor-core
  * B image: image[kd/32][N*32] in the no-swizzle K-major core-matrix order, column n = k*P + plane,
  * value = round(B * mult[k]) written as balanced base-256 digits.  rows >= kd_limit and columns >= P*K are zero.
- * row1/row2 may be NULL.  image2 (optional) receives the planes of B*row1*row2 (the mean-imputation operand
- * mu o D T  of StackedArray.dot's sparse-mask term, lmdec/array/stacked.py:204-217).  */
+ * row1/row2 may be NULL.  With q1 = round(B*row1*mult) and q2 = round(B*row1*row2*mult) (the mean-imputation operand
+ * mu o D T  of StackedArray.dot's sparse-mask term, lmdec/array/stacked.py:204-217), image1 holds q1 and image2
+ * (optional) holds  q2 - 3*q1 : lmdec_geno_matmul multiplies the RAW 2-bit codes (3 at a missing entry) by image1, so
+ * the indicator plane times image2 restores  value.q1 + miss.q2  exactly.  Keep |q2 - 3 q1| below
+ * 127*(256^P - 1)/255 (values are clamped there): with row2 in [0, 2] that means |q1| <= 2^(8P-3).  */
 int lmdec_quantize_planes(const double* B, int64_t ldb, int64_t Kd, int64_t kd_limit, int K, int P, int N,
                           const double* mult, const double* row1, const double* row2, int8_t* image1, int8_t* image2,
                           void* stream);
@@ -87,9 +90,11 @@ int lmdec_colabsmax(const double* B, int64_t ldb, int64_t kd_limit, int K, const
  * ScaledCenterArray.sym_mat_mult / dot (lmdec/array/scaled_legacy.py:379-399, 526-542).
  *   store, M, Kd       the tile store (logical size);  m_limit <= M rows are produced, kd_limit <= Kd is contracted
  *   has_missing        0: every code is 0..2 (one MMA per tile);  1: also run the indicator plane
- *   mode               0: out0 = value.q1 + miss.q2 (q2 = image2, or image1 when image2 is NULL)
+ *   mode               0: out0 = value.q1 + miss.q2 (image2 as written by lmdec_quantize_planes; without image2
+ *                         and with has_missing the result is code.q1, i.e. value.q1 + 3 miss.q1)
  *                      1: out0 = value.q1 ; out1 = miss.q1      (needs has_missing)
- *   splits             split-K factor; 0 = choose; >1 accumulates with int64 atomics (outputs are zeroed here)
+ *   splits             split-K factor; 0 = choose; >1 accumulates with int64 atomics (outputs are zeroed here);
+ *                      a split never spans more than 65,536 contraction elements (int32 accumulators)
  * out0/out1: int64 [m_limit, K] row-major.  */
 int lmdec_geno_matmul(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit, int has_missing,
                       int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N, int64_t* out0,

@@ -2,6 +2,7 @@
 // sm_100a tensor cores (tcgen05.mma kind::i8, accumulators and the decoded A operand in TMEM).
 //
 //   out[m, k] = sum_kd value(m,kd) * q1[kd,k]  (+ miss(m,kd) * q2[kd,k])          exact, int64
+// (the value plane carries raw codes, 3 at a missing entry; image 2 holds q2 - 3 q1 to compensate, see lmdec_b200.h)
 //
 // Replaces the chunked int8->f64 matmuls under PowerMethod._solution_step (reference
 // lmdec/decomp/iter_methods.py:381-386 -> lmdec/array/stacked.py:172-217, chained.py:169-177).
@@ -56,20 +57,20 @@ struct GenoMmaParams {
   int use_atomics;
 };
 
-// 16 codes in r -> 4 words of 4 uint8 each; word k holds codes k, k+4, k+8, k+12 (the B image is permuted to match)
+// 16 codes in r -> 4 words of 4 uint8 each; word k holds codes k, k+4, k+8, k+12 (the B image is permuted to match).
+// The decode is bound by the ALU pipe (LOP3/SHF issue every other cycle per scheduler), so it is written with LEFT
+// shifts only -- ptxas places those on the FMA pipe as IMAD.SHL -- and leaves each code in the TOP two bits of its byte:
+//   value byte  = 64 * code       (code 3 = missing is NOT cleared: the epilogue / the second image subtract 3 * miss)
+//   miss  byte  = 128 * [code==3]
+// The accumulators are therefore exact multiples of 64 / 128 and are shifted back in the epilogue.
+constexpr int kValueShift = 6, kMissShift = 7;
 template <bool kMiss>
 __device__ __forceinline__ void decode16(uint32_t r, uint32_t* v, uint32_t* m) {
-  if (kMiss) {
-    const uint32_t t = r & (r >> 1) & 0x55555555u;  // bit 2i set where code i == 3 (missing)
-    const uint32_t rv = r ^ (t * 3u);               // missing -> dosage 0
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = (rv >> (2 * k)) & 0x03030303u;
-      m[k] = (t >> (2 * k)) & 0x01010101u;
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (r >> (2 * k)) & 0x03030303u;
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t x = (k == 3 ? r : r * (1u << (6 - 2 * k))) & 0xC0C0C0C0u;
+    v[k] = x;
+    if (kMiss) m[k] = x & (x * 2u) & 0x80808080u;
   }
 }
 
@@ -102,7 +103,6 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
   const int K = p.K;
   const int n_groups = (K + 7) / 8;
   const int n_work = p.m_tiles * p.splits;
-  const int n_pass = (p.mode == 1) ? 2 : 1;
   uint32_t tile_no = 0;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
     const int mt = w % p.m_tiles;
@@ -112,41 +112,54 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
     tc_fence_after_sync();
     const long long m = (long long)mt * 128 + row;
     const bool live = m < p.m_limit;
-    for (int pass = 0; pass < n_pass; ++pass) {
-      long long* dst = (pass == 0 ? p.out0 : p.out1) + m * K;
-      for (int g = 0; g < n_groups; ++g) {
-        uint32_t r[8 * P];
-        const uint32_t col = (uint32_t)g * 8 * P;
+    long long* dst0 = p.out0 + m * K;
+    long long* dst1 = p.out1 + m * K;
+    for (int g = 0; g < n_groups; ++g) {
+      uint32_t r0[8 * P], r1[8 * P];
+      const uint32_t col = (uint32_t)g * 8 * P;
 #pragma unroll
-        for (int i = 0; i < P; ++i) tmem_ld8p((p.mode == 1 && pass == 1 ? acc1 : acc0) + col + i * 8, r + 8 * i);
-        if (p.mode == 0) {
-          uint32_t r1[8 * P];
+      for (int i = 0; i < P; ++i) tmem_ld8p(acc0 + col + i * 8, r0 + 8 * i);
 #pragma unroll
-          for (int i = 0; i < P; ++i) tmem_ld8p(acc1 + col + i * 8, r1 + 8 * i);
-          tmem_wait_ld();
+      for (int i = 0; i < P; ++i) tmem_ld8p(acc1 + col + i * 8, r1 + 8 * i);
+      tmem_wait_ld();
+      if (g == n_groups - 1) {
+        // all TMEM reads of this tile are done: hand the accumulator set back to the issuers
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[set]);
+      }
+      // undo the decode's byte scaling (exact: the sums are multiples of 64 / 128)
 #pragma unroll
-          for (int i = 0; i < 8 * P; ++i) r[i] += r1[i];
+      for (int i = 0; i < 8 * P; ++i) {
+        const int a0 = (int)r0[i] >> kValueShift;
+        const int a1 = p.has_missing ? ((int)r1[i] >> kMissShift) : ((int)r1[i] >> kValueShift);
+        if (p.mode == 1) {
+          r0[i] = (uint32_t)(a0 - 3 * a1);  // value plane carried raw codes: code 3 at the missing entries
+          r1[i] = (uint32_t)a1;
         } else {
-          tmem_wait_ld();
+          r0[i] = (uint32_t)(a0 + a1);
         }
-        if (g == n_groups - 1 && pass == n_pass - 1) {
-          // all TMEM reads of this tile are done: hand the accumulator set back to the issuers
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[set]);
-        }
-        if (live) {
+      }
+      if (live) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const int k = g * 8 + kk;
-            if (k < K) {
-              long long acc = (long long)(int)r[kk * P + P - 1];
+        for (int kk = 0; kk < 8; ++kk) {
+          const int k = g * 8 + kk;
+          if (k < K) {
+            long long acc = (long long)(int)r0[kk * P + P - 1];
 #pragma unroll
-              for (int pl = P - 2; pl >= 0; --pl) acc = acc * 256 + (long long)(int)r[kk * P + pl];
+            for (int pl = P - 2; pl >= 0; --pl) acc = acc * 256 + (long long)(int)r0[kk * P + pl];
+            if (p.use_atomics)
+              atomicAdd(reinterpret_cast<unsigned long long*>(dst0 + k), (unsigned long long)acc);
+            else
+              dst0[k] = acc;
+            if (p.mode == 1) {
+              long long am = (long long)(int)r1[kk * P + P - 1];
+#pragma unroll
+              for (int pl = P - 2; pl >= 0; --pl) am = am * 256 + (long long)(int)r1[kk * P + pl];
               if (p.use_atomics)
-                atomicAdd(reinterpret_cast<unsigned long long*>(dst + k), (unsigned long long)acc);
+                atomicAdd(reinterpret_cast<unsigned long long*>(dst1 + k), (unsigned long long)am);
               else
-                dst[k] = acc;
+                dst1[k] = am;
             }
           }
         }
@@ -287,14 +300,19 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     }
   } else if (warp == kIssuerWarp0 || warp == kIssuerWarp0 + 1) {
     // ------------------------------------------------------------------ MMA issuers
-    if (lane == 0) {
+    // The whole warp runs the loop (uniform control flow keeps the operand arithmetic on the uniform datapath); one
+    // elected lane issues.  With a plain `if (lane == 0)` ptxas wraps every UTCIMMA operand in an
+    // ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~100 cycles per MMA, profiles/r01).
+    {
       const int me = warp - kIssuerWarp0;
       const uint32_t idesc = make_idesc_i8(128, (uint32_t)N, 0, 1);
       const uint32_t lbo = (uint32_t)N * 16;
       const uint32_t plane = p.has_missing ? (uint32_t)me : 0u;
       const uint32_t img = (p.has_missing && p.n_img == 2) ? (uint32_t)me : 0u;
       // descriptor of the B ring base; stage / image / K-block offsets are added to its 16-byte address field
-      const uint64_t bdesc_ring = make_smem_desc(smem_u32(smem_b), lbo, 128);
+      const uint64_t bdesc_ring = make_smem_desc(smem_u32(smem_b), lbo, 128) + (uint64_t)((img * img_bytes) >> 4);
+      const uint32_t a_ring = tbase + kARingCol0 + plane * 64;
+      const uint32_t kb_step = (uint32_t)(2 * N);  // one K-block of the image, in 16-byte units
       uint32_t a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       uint32_t tile_no = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
@@ -310,24 +328,24 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
           mbar_wait(&full_a[a_stage], a_phase);
           mbar_wait(&full_b[b_stage], b_phase);
           tc_fence_after_sync();
-          const uint32_t a_addr = tbase + kARingCol0 + a_stage * a_stage_cols + plane * 64;
-          const uint64_t bdesc0 = bdesc_ring + (uint64_t)((b_stage * stage_bytes + img * img_bytes) >> 4);
-          if (p.has_missing) {
+          const uint32_t a_addr = a_ring + a_stage * a_stage_cols;
+          const uint64_t bdesc0 = bdesc_ring + (uint64_t)((b_stage * stage_bytes) >> 4);
+          if (elect_one()) {
+            if (p.has_missing) {
+              umma_ts_i8(d_addr, a_addr, bdesc0, idesc, accumulate);
 #pragma unroll
-            for (int j = 0; j < kKbPerChunk; ++j) {
-              umma_ts_i8(d_addr, a_addr + j * 8, bdesc0 + (uint64_t)(j * 2 * N), idesc, accumulate);
-              accumulate = 1;
-            }
-          } else {
+              for (int j = 1; j < kKbPerChunk; ++j) umma_ts_i8(d_addr, a_addr + j * 8, bdesc0 + j * kb_step, idesc, 1u);
+            } else {
+              umma_ts_i8(d_addr, a_addr + me * 8, bdesc0 + me * kb_step, idesc, accumulate);
 #pragma unroll
-            for (int j = 0; j < kKbPerChunk / 2; ++j) {
-              const int jj = 2 * j + me;
-              umma_ts_i8(d_addr, a_addr + jj * 8, bdesc0 + (uint64_t)(jj * 2 * N), idesc, accumulate);
-              accumulate = 1;
+              for (int j = 1; j < kKbPerChunk / 2; ++j)
+                umma_ts_i8(d_addr, a_addr + (2 * j + me) * 8, bdesc0 + (2 * j + me) * kb_step, idesc, 1u);
             }
+            umma_commit(&empty_a[a_stage]);
+            umma_commit(&empty_b[b_stage]);
           }
-          umma_commit(&empty_a[a_stage]);
-          umma_commit(&empty_b[b_stage]);
+          __syncwarp();
+          accumulate = 1;
           if (++a_stage == (uint32_t)a_stages) {
             a_stage = 0;
             a_phase ^= 1;
@@ -337,7 +355,8 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
             b_phase ^= 1;
           }
         }
-        umma_commit(&acc_full[set]);
+        if (elect_one()) umma_commit(&acc_full[set]);
+        __syncwarp();
       }
     }
   } else {

@@ -225,26 +225,35 @@ __global__ void quantize_planes_kernel(const double* __restrict__ B, int64_t ldb
   if (n < K * P) {
     const int k = n / P, pl = n - k * P;  // column n = k*P + plane (geno_mma.cuh epilogue_loop)
     const double mk = mult[k];
-    const double lim = ldexp(1.0, 8 * P - 2);
+    // largest magnitude P balanced base-256 digits can hold: 127 * (256^P - 1) / 255
+    const double qmax = 127.0 * (ldexp(1.0, 8 * P) - 1.0) / 255.0;
 #pragma unroll 4
     for (int e = 0; e < 16; ++e) {
       const int64_t g = kb * 32 + 16 * h + (e >> 2) + 4 * (e & 3);
       if (g < kd_limit) {
         double x = B[g * ldb + k] * mk;
         if (row1) x *= row1[g];
-        for (int im = 0; im < 2; ++im) {
-          if (im == 1) {
-            if (!image2) break;
-            x *= row2[g];
-          }
-          double xc = fmin(fmax(x, -lim), lim);
-          long long qv = llrint(xc);
+        long long q1 = llrint(fmin(fmax(x, -qmax), qmax));
+        {
+          long long qv = q1;
           int d = 0;
           for (int i = 0; i <= pl; ++i) {
             d = (int)(signed char)(qv & 255);
             qv = (qv - d) >> 8;
           }
-          (im == 0 ? o1 : o2)[e >> 2] |= (uint32_t)(d & 255) << (8 * (e & 3));
+          o1[e >> 2] |= (uint32_t)(d & 255) << (8 * (e & 3));
+        }
+        if (image2) {
+          // the product kernel multiplies RAW codes (3 at a missing entry) by image 1: image 2 carries q2 - 3 q1
+          const double x2 = x * row2[g];
+          long long qv = llrint(fmin(fmax(x2, -qmax), qmax)) - 3 * q1;
+          qv = qv > (long long)qmax ? (long long)qmax : (qv < -(long long)qmax ? -(long long)qmax : qv);
+          int d = 0;
+          for (int i = 0; i <= pl; ++i) {
+            d = (int)(signed char)(qv & 255);
+            qv = (qv - d) >> 8;
+          }
+          o2[e >> 2] |= (uint32_t)(d & 255) << (8 * (e & 3));
         }
       }
     }
@@ -519,9 +528,9 @@ int lmdec_geno_matmul(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_lim
   p.out0 = (long long*)out0;
   p.out1 = (long long*)out1;
   // split-K: minimise the makespan  ceil(work / SMs) * (chunks per split + per-item overhead)  over the split count;
-  // the int32 accumulators cap a split at 8192 chunks (8192 * 256 * 2 * 127 < 2^30)
+  // the int32 accumulators cap a split at 256 chunks (value bytes are 64*code: 64 * 3 * 127 * 65536 < 2^31)
   int want = splits;
-  const int min_splits = (int)cdiv(p.n_chunks, 8192);
+  const int min_splits = (int)cdiv(p.n_chunks, 256);
   if (want <= 0) {
     const int max_s = p.n_chunks / 4 > 1 ? (p.n_chunks / 4 < 256 ? p.n_chunks / 4 : 256) : 1;
     long long best = -1;

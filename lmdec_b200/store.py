@@ -291,7 +291,8 @@ class GenotypeOperator:
 
     def _mult(self, b, two):
         s = torch.maximum(b["amax"], b["amax2"]) if two else b["amax"]
-        lim = float(2.0 ** (8 * self.planes - 2))
+        # |q1| <= 2^(8P-2); one bit less when the second image (q2 - 3 q1, |.| <= 3 |q1|) is produced
+        lim = float(2.0 ** (8 * self.planes - (3 if two else 2)))
         # a zero column quantises to zero with any multiplier; inf/NaN columns poison the result on purpose
         return torch.where(s > 0, lim / s, torch.ones_like(s))
 

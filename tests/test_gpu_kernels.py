@@ -98,10 +98,10 @@ def test_geno_matmul_exact(cuda, M, Kd, K, P, miss, mode, splits):
     np.testing.assert_array_equal(amax.cpu().numpy(), np.abs(B * r1[:, None]).max(0))
     np.testing.assert_array_equal(amax2.cpu().numpy(), np.abs(B * r1[:, None] * r2[:, None]).max(0))
     scale = np.maximum(amax.cpu().numpy(), amax2.cpu().numpy())
-    mult = (2.0 ** (8 * P - 2)) / scale
-    multd = torch.from_numpy(mult).to(cuda)
     has_missing = int(miss > 0)
     two_images = has_missing and mode == 0
+    mult = (2.0 ** (8 * P - (3 if two_images else 2))) / scale
+    multd = torch.from_numpy(mult).to(cuda)
     im1, im2 = _quantize(torch, capi, lib, Bd, Kd, K, P, N, multd, r1d, r2d if two_images else None)
     out0 = torch.full((M, K), -7, dtype=torch.int64, device=cuda)
     out1 = torch.full((M, K), -7, dtype=torch.int64, device=cuda)
