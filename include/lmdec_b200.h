@@ -121,6 +121,36 @@ int lmdec_qvals(const double* si, const double* sj, int k, int scale, double* ou
 int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, const double* s, int64_t m, int K,
                  double* out, double* work /* >= 592 doubles */, void* stream);
 
+/* One application of the genotype operator, all kernels enqueued back to back (no host work in between):
+ *   transpose = 0:  out[m_limit, K] = A B        A = ((G + M) - 1 mu^T) D,  B is [Kd = p, K]
+ *   transpose = 1:  out[m_limit, K] = A^T B      store is the SNP-major one (M = p),  B is [Kd = n, K]
+ * i.e. `.dot` / `.T.dot` of the operator make_snp_array builds (lmdec/decomp/utils.py:280-287) as called by
+ * PowerMethod._solution_step (lmdec/decomp/iter_methods.py:383), v_init (init_methods.py:33), subspace_to_V
+ * (matrix_ops.py:93) and rmse_k (metrics.py:157).
+ *   scale     D = 1/std per SNP, or NULL;  impute  mu per SNP (needed when has_missing);
+ *   center_w  NULL = no centring; else (mu o D) per SNP  [transpose = 1 multiplies it by sum_i B_ik, transpose = 0
+ *             contracts it with B]
+ *   work      lmdec_apply_work_doubles(K) doubles;  image1/2, acc0/1: caller-owned scratch (lmdec_image_bytes(Kd, N)
+ *             with N = 16*ceil(K*P/16);  int64 [m_limit, K])
+ * Steps: column statistics of B (max for the fixed-point scale, weighted column sum for the rank-1 term), plane
+ * quantisation, lmdec_geno_matmul, lmdec_finalize.  */
+int64_t lmdec_apply_work_doubles(int K);
+int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
+                         int has_missing, int transpose, const double* B, int64_t ldb, int K, int P,
+                         const double* scale, const double* impute, const double* center_w, double* work,
+                         int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, double* out, int64_t ldo,
+                         void* stream);
+
+/* K x K Cholesky whitening on the device (one block, float64): G = r^T r, r upper triangular, r_inv = r^-1.
+ * *flag (int32, device) = 1 when G is not numerically positive definite (pivot of the unit-diagonal-scaled matrix below
+ * rank_tol, or non-finite input): the host then takes its rank-revealing path.  The K x K step of CholeskyQR2, in
+ * place of dask tsqr's stacked-R QR (lmdec/decomp/iter_methods.py:382).  */
+int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, double* r, int* flag, void* stream);
+
+/* CUDA-event timing of lmdec_geno_matmul's kernel on its launching stream (bench.py's roofline figure). */
+void lmdec_kernel_timing(int on);
+int lmdec_kernel_timing_read(double* total_ms_host, int64_t* launches_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,12 @@ SIGNATURES = {
     "lmdec_gram_work_doubles": (_i64, [_i64, _i32]),
     "lmdec_gram": (_i32, [_p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p]),
     "lmdec_qvals": (_i32, [_p, _p, _i32, _i32, _p, _p]),
+    "lmdec_apply_work_doubles": (_i64, [_i32]),
+    "lmdec_operator_apply": (_i32, [_p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p,
+                                    _p, _p, _p, _i64, _p]),
+    "lmdec_chol_whiten": (_i32, [_p, _i32, C.c_double, _p, _p, _p, _p]),
+    "lmdec_kernel_timing": (None, [_i32]),
+    "lmdec_kernel_timing_read": (_i32, [_p, _p]),
     "lmdec_sqdiff": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p]),
 }
 

@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ..device import F64, gram
+from ..device import F64, chol_whiten, gram
 
 
 def _allreduce(t: torch.Tensor, group):
@@ -64,6 +64,10 @@ def orthonormalize(x: torch.Tensor, group=None, seed: int = 0, gram_fn=None):
     if x.ndim != 2:
         raise ValueError("expected a 2-D iterate")
     K = x.shape[1]
+    if gram_fn is None and x.is_cuda and K <= 128:
+        fast = _orthonormalize_device(x, group)
+        if fast is not None:
+            return fast
     r_total = np.eye(K)
     q = x
     gram_fn = gram_fn or gram      # the device kernel; tests of the host logic pass a CPU stand-in
@@ -83,6 +87,24 @@ def orthonormalize(x: torch.Tensor, group=None, seed: int = 0, gram_fn=None):
             # the refilled columns carry no part of x: zero rows of r
             r_total[dead, :] = 0.0
     return q, r_total
+
+
+def _orthonormalize_device(x: torch.Tensor, group=None):
+    """CholeskyQR2 with both K x K factorizations on the device and ONE device->host copy (r and the health flags).
+    Returns None when the iterate is not numerically full rank / finite: the caller then takes the host path."""
+    K = x.shape[1]
+    G1 = _allreduce(gram(x), group)
+    ri1, r1, f1 = chol_whiten(G1)
+    q1 = x @ ri1
+    G2 = _allreduce(gram(q1), group)
+    ri2, r2, f2 = chol_whiten(G2)
+    q = q1 @ ri2
+    r = r2 @ r1
+    dev2 = (G2 - torch.eye(K, dtype=F64, device=x.device)).abs().max().reshape(1)
+    host = torch.cat([r.reshape(-1), f1.to(F64), f2.to(F64), dev2]).cpu().numpy()
+    if host[K * K] != 0 or host[K * K + 1] != 0 or not (host[K * K + 2] < 1e-2):
+        return None
+    return q, host[:K * K].reshape(K, K)
 
 
 def tsqr_svd(x: torch.Tensor, group=None):

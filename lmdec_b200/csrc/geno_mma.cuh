@@ -37,6 +37,17 @@ constexpr int kMaxBStages = 4;
 constexpr int kMaxTileStages = 8;
 constexpr uint32_t kTileBytes = 8192;
 
+// out[m,k] = (acc0 + rowa[m]*acc1) * colscale[k] * rowscale[m] + rowshift[m] * colshift[k]   (NULL = absent / 1)
+struct FusedFinalize {
+  const double* colscale;
+  const double* colshift;
+  const double* rowa;
+  const double* rowscale;
+  const double* rowshift;
+  double* out;
+  long long ldo;
+};
+
 struct GenoMmaParams {
   const uint8_t* store;
   long long store_kc;      // chunks per row panel in the store (tile stride)
@@ -55,6 +66,8 @@ struct GenoMmaParams {
   int b_stages;
   int tile_stages;
   int use_atomics;
+  int fuse;                // write the finalized float64 result from the epilogue (never with atomics)
+  FusedFinalize fz;
 };
 
 // 16 codes in r -> 4 words of 4 uint8 each; word k holds codes k, k+4, k+8, k+12 (the B image is permuted to match).
@@ -114,6 +127,14 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
     const bool live = m < p.m_limit;
     long long* dst0 = p.out0 + m * K;
     long long* dst1 = p.out1 + m * K;
+    double row_a = 0.0, row_scale = 1.0, row_shift = 1.0;
+    double* fdst = nullptr;
+    if (p.fuse && live) {
+      if (p.fz.rowa) row_a = p.fz.rowa[m];
+      if (p.fz.rowscale) row_scale = p.fz.rowscale[m];
+      if (p.fz.rowshift) row_shift = p.fz.rowshift[m];
+      fdst = p.fz.out + m * p.fz.ldo;
+    }
     for (int g = 0; g < n_groups; ++g) {
       uint32_t r0[8 * P], r1[8 * P];
       const uint32_t col = (uint32_t)g * 8 * P;
@@ -148,6 +169,19 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
             long long acc = (long long)(int)r0[kk * P + P - 1];
 #pragma unroll
             for (int pl = P - 2; pl >= 0; --pl) acc = acc * 256 + (long long)(int)r0[kk * P + pl];
+            if (p.fuse) {
+              double v = (double)acc;
+              if (p.mode == 1) {
+                long long am = (long long)(int)r1[kk * P + P - 1];
+#pragma unroll
+                for (int pl = P - 2; pl >= 0; --pl) am = am * 256 + (long long)(int)r1[kk * P + pl];
+                v += row_a * (double)am;
+              }
+              v *= __ldg(p.fz.colscale + k) * row_scale;
+              if (p.fz.colshift) v += row_shift * __ldg(p.fz.colshift + k);
+              fdst[k] = v;
+              continue;
+            }
             if (p.use_atomics)
               atomicAdd(reinterpret_cast<unsigned long long*>(dst0 + k), (unsigned long long)acc);
             else

@@ -5,6 +5,8 @@
 #include <cstring>
 #include <cmath>
 #include <atomic>
+#include <vector>
+#include <utility>
 #include "../../include/lmdec_b200.h"
 #include "geno_mma.cuh"
 
@@ -26,6 +28,9 @@ int check_launch(const char* what, int n_kernels = 1) {
 }
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 }  // namespace
+
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_mma_events;
+static bool g_mma_timing = false;
 
 namespace lmdec {
 
@@ -208,58 +213,78 @@ __global__ void store_transpose_kernel(const uint8_t* __restrict__ src, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------------ operand planes
-// one thread = one 16-byte unit of the image: fixed (K-block kb, half h, column n), 16 contraction positions.
-// byte e of the unit is MMA contraction index 16h + e, which the producers' decode maps to genotype position
-// 16h + (e>>2) + 4*(e&3) of the K-block (geno_mma.cuh decode16).
-__global__ void quantize_planes_kernel(const double* __restrict__ B, int64_t ldb, int64_t kd_limit, int K, int P, int N,
-                                       const double* __restrict__ mult, const double* __restrict__ row1,
-                                       const double* __restrict__ row2, int8_t* __restrict__ image1,
-                                       int8_t* __restrict__ image2, int64_t n_units) {
-  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (unit >= n_units) return;
-  const int n = (int)(unit % N);
-  const int64_t kbh = unit / N;
-  const int h = (int)(kbh & 1);
-  const int64_t kb = kbh >> 1;
-  uint32_t o1[4] = {0, 0, 0, 0}, o2[4] = {0, 0, 0, 0};
-  if (n < K * P) {
-    const int k = n / P, pl = n - k * P;  // column n = k*P + plane (geno_mma.cuh epilogue_loop)
+// one thread = 16 contraction positions (K-block kb, half h) x one operand column k: it reads its 16 values once and
+// writes the P plane units of image 1 (and of image 2).  Unit (kb, h, n) sits at ((kb*2 + h)*N + n)*16 bytes; byte e of
+// a unit is MMA contraction index 16h + e, which the producers' decode maps to genotype position
+// 16h + (e>>2) + 4*(e&3) of the K-block (geno_mma.cuh decode16).  Column n = k*P + plane.
+template <int P>
+__global__ void __launch_bounds__(256) quantize_planes_kernel(const double* __restrict__ B, int64_t ldb,
+                                                              int64_t kd_limit, int K, int N,
+                                                              const double* __restrict__ mult,
+                                                              const double* __restrict__ row1,
+                                                              const double* __restrict__ row2,
+                                                              int8_t* __restrict__ image1, int8_t* __restrict__ image2,
+                                                              int64_t n_groups) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int kq = N / P;                       // columns handled per group: k < K real, K <= k < kq zero padding
+  if (idx >= n_groups * kq) return;
+  const int k = (int)(idx % kq);
+  const int64_t grp = idx / kq;               // grp = kb*2 + h
+  uint32_t o1[P][4], o2[P][4];
+#pragma unroll
+  for (int pl = 0; pl < P; ++pl)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o1[pl][j] = o2[pl][j] = 0;
+  if (k < K) {
     const double mk = mult[k];
     // largest magnitude P balanced base-256 digits can hold: 127 * (256^P - 1) / 255
     const double qmax = 127.0 * (ldexp(1.0, 8 * P) - 1.0) / 255.0;
-#pragma unroll 4
+    const int64_t g0 = grp * 16;
+#pragma unroll
     for (int e = 0; e < 16; ++e) {
-      const int64_t g = kb * 32 + 16 * h + (e >> 2) + 4 * (e & 3);
+      const int64_t g = g0 + (e >> 2) + 4 * (e & 3);
       if (g < kd_limit) {
         double x = B[g * ldb + k] * mk;
         if (row1) x *= row1[g];
-        long long q1 = llrint(fmin(fmax(x, -qmax), qmax));
-        {
-          long long qv = q1;
-          int d = 0;
-          for (int i = 0; i <= pl; ++i) {
-            d = (int)(signed char)(qv & 255);
-            qv = (qv - d) >> 8;
-          }
-          o1[e >> 2] |= (uint32_t)(d & 255) << (8 * (e & 3));
+        const long long q1 = llrint(fmin(fmax(x, -qmax), qmax));
+        long long qv = q1;
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl) {
+          const int d = (int)(signed char)(qv & 255);
+          qv = (qv - d) >> 8;
+          o1[pl][e >> 2] |= (uint32_t)(d & 255) << (8 * (e & 3));
         }
         if (image2) {
           // the product kernel multiplies RAW codes (3 at a missing entry) by image 1: image 2 carries q2 - 3 q1
-          const double x2 = x * row2[g];
-          long long qv = llrint(fmin(fmax(x2, -qmax), qmax)) - 3 * q1;
+          qv = llrint(fmin(fmax(x * row2[g], -qmax), qmax)) - 3 * q1;
           qv = qv > (long long)qmax ? (long long)qmax : (qv < -(long long)qmax ? -(long long)qmax : qv);
-          int d = 0;
-          for (int i = 0; i <= pl; ++i) {
-            d = (int)(signed char)(qv & 255);
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl) {
+            const int d = (int)(signed char)(qv & 255);
             qv = (qv - d) >> 8;
+            o2[pl][e >> 2] |= (uint32_t)(d & 255) << (8 * (e & 3));
           }
-          o2[e >> 2] |= (uint32_t)(d & 255) << (8 * (e & 3));
         }
       }
     }
   }
-  *reinterpret_cast<uint4*>(image1 + unit * 16) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-  if (image2) *reinterpret_cast<uint4*>(image2 + unit * 16) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  const size_t base = ((size_t)grp * N + (size_t)k * P) * 16;
+#pragma unroll
+  for (int pl = 0; pl < P; ++pl) {
+    *reinterpret_cast<uint4*>(image1 + base + pl * 16) = make_uint4(o1[pl][0], o1[pl][1], o1[pl][2], o1[pl][3]);
+    if (image2)
+      *reinterpret_cast<uint4*>(image2 + base + pl * 16) = make_uint4(o2[pl][0], o2[pl][1], o2[pl][2], o2[pl][3]);
+  }
+}
+// columns [ (N/P)*P, N ) are not covered by the groups above when P does not divide N: zero them
+__global__ void quantize_tail_kernel(int8_t* __restrict__ image1, int8_t* __restrict__ image2, int N, int n0,
+                                     int64_t n_groups) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = N - n0;
+  if (idx >= n_groups * w) return;
+  const size_t off = ((size_t)(idx / w) * N + n0 + (idx % w)) * 16;
+  *reinterpret_cast<uint4*>(image1 + off) = make_uint4(0, 0, 0, 0);
+  if (image2) *reinterpret_cast<uint4*>(image2 + off) = make_uint4(0, 0, 0, 0);
 }
 
 __global__ void colabsmax_kernel(const double* __restrict__ B, int64_t ldb, int64_t kd_limit, int K,
@@ -277,6 +302,85 @@ __global__ void colabsmax_kernel(const double* __restrict__ B, int64_t ldb, int6
   }
   atomicMax(out + k, (unsigned long long)__double_as_longlong(m1));
   if (row2) atomicMax(out2 + k, (unsigned long long)__double_as_longlong(m2));
+}
+
+// Column statistics of a float64 operand in one pass: max |B r1|, max |B r1 r2| and sum_r w_r B_rk per column.
+// Deterministic: per-block partials (fixed row -> block map) reduced in block order by colstats_finish_kernel, which
+// also derives the fixed-point multiplier, its inverse and the rank-1 shift used by the finalize kernel.
+constexpr int kStatsMaxBlocks = 1184;
+__global__ void __launch_bounds__(256) colstats_partial_kernel(const double* __restrict__ B, int64_t ldb,
+                                                               int64_t kd_limit, int K, const double* __restrict__ row1,
+                                                               const double* __restrict__ row2,
+                                                               const double* __restrict__ w, int use_w,
+                                                               double* __restrict__ partial) {
+  extern __shared__ double sm[];
+  const int k = threadIdx.x % K, ry = threadIdx.x / K, rpb = blockDim.x / K;
+  double m1 = 0.0, m2 = 0.0, ws = 0.0;
+  if (ry < rpb) {
+    for (int64_t r = (int64_t)blockIdx.x * rpb + ry; r < kd_limit; r += (int64_t)gridDim.x * rpb) {
+      const double b = B[r * ldb + k];
+      double v = fabs(b);
+      if (row1) v *= fabs(row1[r]);
+      if (v != v) v = INFINITY;  // NaN poisons the scale: the Gram check on the host side raises LinAlgError
+      m1 = fmax(m1, v);
+      if (row2) m2 = fmax(m2, v * fabs(row2[r]));
+      if (use_w) ws += (w ? w[r] : 1.0) * b;
+    }
+  }
+  double* s1 = sm;
+  double* s2 = sm + blockDim.x;
+  double* s3 = sm + 2 * blockDim.x;
+  s1[threadIdx.x] = m1;
+  s2[threadIdx.x] = m2;
+  s3[threadIdx.x] = ws;
+  __syncthreads();
+  if (threadIdx.x < K) {
+    for (int j = 1; j < rpb; ++j) {
+      m1 = fmax(m1, s1[j * K + k]);
+      m2 = fmax(m2, s2[j * K + k]);
+      ws += s3[j * K + k];
+    }
+    double* out = partial + (size_t)blockIdx.x * 3 * K;
+    out[k] = m1;
+    out[K + k] = m2;
+    out[2 * K + k] = ws;
+  }
+}
+// stats layout: [0,K) mult, [K,2K) 1/mult, [2K,3K) shift = shift_sign * wsum, [3K,4K) amax, [4K,5K) amax2
+// 1024 threads: thread (slice, k) folds blocks slice, slice+S, ... ; thread k then folds the slices in order.
+__global__ void __launch_bounds__(1024) colstats_finish_kernel(const double* __restrict__ partial, int n_blocks, int K,
+                                                               double lim, double shift_sign,
+                                                               double* __restrict__ stats) {
+  extern __shared__ double sm[];
+  const int n_sl = blockDim.x / K;
+  const int k = threadIdx.x % K, sl = threadIdx.x / K;
+  double m1 = 0.0, m2 = 0.0, ws = 0.0;
+  if (sl < n_sl) {
+    for (int b = sl; b < n_blocks; b += n_sl) {
+      const double* in = partial + (size_t)b * 3 * K;
+      m1 = fmax(m1, in[k]);
+      m2 = fmax(m2, in[K + k]);
+      ws += in[2 * K + k];
+    }
+    sm[(sl * 3 + 0) * K + k] = m1;
+    sm[(sl * 3 + 1) * K + k] = m2;
+    sm[(sl * 3 + 2) * K + k] = ws;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    for (int j = 1; j < n_sl; ++j) {
+      m1 = fmax(m1, sm[(j * 3 + 0) * K + k]);
+      m2 = fmax(m2, sm[(j * 3 + 1) * K + k]);
+      ws += sm[(j * 3 + 2) * K + k];
+    }
+    const double s_ = fmax(m1, m2);
+    const double mult = s_ > 0.0 ? lim / s_ : 1.0;  // a zero column quantises to zero with any multiplier
+    stats[k] = mult;
+    stats[K + k] = 1.0 / mult;
+    stats[2 * K + k] = shift_sign * ws;
+    stats[3 * K + k] = m1;
+    stats[4 * K + k] = m2;
+  }
 }
 
 __global__ void finalize_kernel(const long long* __restrict__ acc0, const long long* __restrict__ acc1, int64_t M, int K,
@@ -347,6 +451,69 @@ __global__ void gram_final_kernel(const double* __restrict__ work, int n_blocks,
     G[o] = a;
   else if (colsum)
     colsum[o - K * K] = a;
+}
+
+// K x K Cholesky whitening in one block (float64, shared memory): G = R^T R with G scaled to unit diagonal first.
+//   r_inv [K,K] and r [K,K] row-major (upper triangular), flag = 1 when G is non-finite, has a non-positive diagonal or
+//   a pivot below rank_tol (the caller then takes the rank-revealing host path).  Replaces the K x K step of dask tsqr
+//   (lmdec/decomp/iter_methods.py:382) without a device->host round trip.
+__global__ void __launch_bounds__(128) chol_whiten_kernel(const double* __restrict__ G, int K, double rank_tol,
+                                                          double* __restrict__ r_inv, double* __restrict__ r,
+                                                          int* __restrict__ flag) {
+  extern __shared__ double sm[];
+  double* L = sm;            // [K][K] lower factor of the scaled Gram matrix
+  double* Li = sm + K * K;   // [K][K] inverse of L (lower)
+  double* d = sm + 2 * K * K;
+  __shared__ int bad;
+  const int t = threadIdx.x;
+  if (t == 0) bad = 0;
+  __syncthreads();
+  if (t < K) {
+    const double g = G[t * K + t];
+    if (!(g > 0.0) || !isfinite(g)) bad = 1;
+    d[t] = (g > 0.0 && isfinite(g)) ? sqrt(g) : 1.0;
+  }
+  __syncthreads();
+  for (int i = t; i < K * K; i += blockDim.x) {
+    const int a = i / K, b = i - a * K;
+    const double v = 0.5 * (G[a * K + b] + G[b * K + a]) / (d[a] * d[b]);
+    if (!isfinite(v)) bad = 1;
+    L[i] = v;
+    Li[i] = 0.0;
+  }
+  __syncthreads();
+  // right-looking Cholesky: thread t owns row t
+  for (int j = 0; j < K; ++j) {
+    if (t == j) {
+      const double piv = L[j * K + j];
+      if (!(piv >= rank_tol)) bad = 1;
+      L[j * K + j] = sqrt(piv > rank_tol ? piv : rank_tol);
+    }
+    __syncthreads();
+    if (t > j && t < K) L[t * K + j] /= L[j * K + j];
+    __syncthreads();
+    if (t > j && t < K) {
+      const double ltj = L[t * K + j];
+      for (int c = j + 1; c <= t; ++c) L[t * K + c] -= ltj * L[c * K + j];
+    }
+    __syncthreads();
+  }
+  // inverse of the lower factor by forward substitution: thread t owns column t of Li
+  if (t < K) {
+    for (int i = t; i < K; ++i) {
+      double acc = (i == t) ? 1.0 : 0.0;
+      for (int c = t; c < i; ++c) acc -= L[i * K + c] * Li[c * K + t];
+      Li[i * K + t] = acc / L[i * K + i];
+    }
+  }
+  __syncthreads();
+  // G = D L L^T D  =>  r = L^T D (upper),  r_inv = D^-1 L^-T (upper)
+  for (int i = t; i < K * K; i += blockDim.x) {
+    const int a = i / K, b = i - a * K;  // element (a, b)
+    r[i] = (b >= a) ? L[b * K + a] * d[b] : 0.0;
+    r_inv[i] = (b >= a) ? Li[b * K + a] / d[a] : 0.0;
+  }
+  if (t == 0) *flag = bad;
 }
 
 __global__ void qvals_kernel(const double* __restrict__ si, const double* __restrict__ sj, int k, int scale,
@@ -474,9 +641,19 @@ int lmdec_quantize_planes(const double* B, int64_t ldb, int64_t Kd, int64_t kd_l
     return fail("lmdec_quantize_planes: need 1<=P<=4, N%16==0, 16<=N<=128, K*P<=N");
   if (image2 && !row2) return fail("lmdec_quantize_planes: image2 needs row2");
   if (kd_limit > Kd) return fail("lmdec_quantize_planes: kd_limit > Kd");
-  const int64_t n_units = cdiv(Kd, 256) * 8 * 2 * N;
-  quantize_planes_kernel<<<(unsigned)cdiv(n_units, 256), 256, 0, (cudaStream_t)stream>>>(
-      B, ldb, kd_limit, K, P, N, mult, row1, row2, image1, image2, n_units);
+  const int64_t n_groups = cdiv(Kd, 256) * 8 * 2;
+  const int kq = N / P;
+  const unsigned blocks = (unsigned)cdiv(n_groups * kq, 256);
+  cudaStream_t st_ = (cudaStream_t)stream;
+  switch (P) {
+    case 1: quantize_planes_kernel<1><<<blocks, 256, 0, st_>>>(B, ldb, kd_limit, K, N, mult, row1, row2, image1, image2, n_groups); break;
+    case 2: quantize_planes_kernel<2><<<blocks, 256, 0, st_>>>(B, ldb, kd_limit, K, N, mult, row1, row2, image1, image2, n_groups); break;
+    case 3: quantize_planes_kernel<3><<<blocks, 256, 0, st_>>>(B, ldb, kd_limit, K, N, mult, row1, row2, image1, image2, n_groups); break;
+    default: quantize_planes_kernel<4><<<blocks, 256, 0, st_>>>(B, ldb, kd_limit, K, N, mult, row1, row2, image1, image2, n_groups); break;
+  }
+  if (kq * P < N)
+    quantize_tail_kernel<<<(unsigned)cdiv(n_groups * (N - kq * P), 256), 256, 0, st_>>>(image1, image2, N, kq * P,
+                                                                                        n_groups);
   return check_launch("lmdec_quantize_planes");
 }
 
@@ -496,9 +673,13 @@ int lmdec_colabsmax(const double* B, int64_t ldb, int64_t kd_limit, int K, const
   return check_launch("lmdec_colabsmax");
 }
 
-int lmdec_geno_matmul(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit, int has_missing,
-                      int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N, int64_t* out0,
-                      int64_t* out1, int splits, void* stream) {
+}  // extern "C"
+
+// fz (optional): finalize fused into the epilogue when the product is not split; *fused reports whether it was
+static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
+                           int has_missing, int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N,
+                           int64_t* out0, int64_t* out1, int splits, void* stream, const FusedFinalize* fz,
+                           bool* fused) {
   if (N % 16 || N < 16 || N > 128 || K * P > N || P < 1 || P > 4) return fail("lmdec_geno_matmul: bad K/P/N");
   if (m_limit <= 0 || m_limit > M || kd_limit <= 0 || kd_limit > Kd) return fail("lmdec_geno_matmul: bad limits");
   if (mode == 1 && (!has_missing || !out1)) return fail("lmdec_geno_matmul: mode 1 needs has_missing and out1");
@@ -549,6 +730,12 @@ int lmdec_geno_matmul(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_lim
   const int cps = (int)cdiv(p.n_chunks, want);
   p.splits = (int)cdiv(p.n_chunks, cps);
   p.use_atomics = p.splits > 1;
+  if (fused) *fused = false;
+  if (fz && !p.use_atomics) {
+    p.fz = *fz;
+    p.fuse = 1;
+    if (fused) *fused = true;
+  }
   const size_t stage_bytes = (size_t)8 * N * 32 * p.n_img;
   const size_t scratch = 0;
   const size_t budget = 225 * 1024;  // 227 KB per CTA minus static barriers and alignment slack
@@ -574,8 +761,27 @@ int lmdec_geno_matmul(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_lim
   }
   const int n_work = p.m_tiles * p.splits;
   const int grid = n_work < n_sm ? n_work : n_sm;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_mma_timing) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+  }
   geno_mma_kernel<<<grid, kThreads, smem, st>>>(p);
+  if (g_mma_timing) {
+    cudaEventRecord(ev1, st);
+    g_mma_events.emplace_back(ev0, ev1);
+  }
   return check_launch("lmdec_geno_matmul");
+}
+
+extern "C" {
+
+int lmdec_geno_matmul(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit, int has_missing,
+                      int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N, int64_t* out0,
+                      int64_t* out1, int splits, void* stream) {
+  return launch_geno_mma(store, M, Kd, m_limit, kd_limit, has_missing, mode, image1, image2, K, P, N, out0, out1,
+                         splits, stream, nullptr, nullptr);
 }
 
 int lmdec_finalize(const int64_t* acc0, const int64_t* acc1, int64_t M, int K, const double* colscale,
@@ -625,6 +831,93 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
   sqdiff_partial_kernel<<<(unsigned)nb, 256, 0, st>>>(A, lda, B, ldb_, s, m, K, work);
   sum_final_kernel<<<1, 32, 0, st>>>(work, (int)nb, out);
   return check_launch("lmdec_sqdiff", 2);
+}
+
+int64_t lmdec_apply_work_doubles(int K) { return (int64_t)5 * K + (int64_t)kStatsMaxBlocks * 3 * K; }
+
+int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
+                         int has_missing, int transpose, const double* B, int64_t ldb, int K, int P,
+                         const double* scale, const double* impute, const double* center_w, double* work,
+                         int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, double* out, int64_t ldo,
+                         void* stream) {
+  if (K < 1 || K > 128 || P < 1 || P > 4) return fail("lmdec_operator_apply: bad K/P");
+  const int N = (K * P + 15) / 16 * 16;
+  if (N > 128) return fail("lmdec_operator_apply: K*P needs more than 128 tensor-core columns");
+  if (has_missing && !impute) return fail("lmdec_operator_apply: has_missing needs the imputation vector");
+  if (has_missing && ((!transpose && !image2) || (transpose && !acc1)))
+    return fail("lmdec_operator_apply: has_missing needs image2 (A.dot) / acc1 (A.T.dot)");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* stats = work;
+  double* partial = work + 5 * K;
+  const bool two = has_missing && !transpose;
+  // ---- column statistics -> fixed-point multiplier and rank-1 shift
+  const int rpb = 256 / K > 0 ? 256 / K : 1;
+  int64_t blocks = cdiv(kd_limit, (int64_t)rpb * 8);
+  if (blocks > kStatsMaxBlocks) blocks = kStatsMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  const int threads = 256;
+  const double lim = ldexp(1.0, 8 * P - (two ? 3 : 2));
+  colstats_partial_kernel<<<(unsigned)blocks, threads, 3 * threads * sizeof(double), st>>>(
+      B, ldb, kd_limit, K, transpose ? nullptr : scale, two ? impute : nullptr, transpose ? nullptr : center_w,
+      center_w != nullptr, partial);
+  colstats_finish_kernel<<<1, 1024, (size_t)(1024 / K) * 3 * K * sizeof(double), st>>>(partial, (int)blocks, K, lim,
+                                                                                          -1.0, stats);
+  int rc = check_launch("lmdec_operator_apply (colstats)", 2);
+  if (rc) return rc;
+  // ---- int8 planes
+  rc = lmdec_quantize_planes(B, ldb, Kd, kd_limit, K, P, N, stats, transpose ? nullptr : scale,
+                             two ? impute : nullptr, image1, two ? image2 : nullptr, stream);
+  if (rc) return rc;
+  // ---- tensor-core product, with the diagonal / rank-1 terms fused into its epilogue when it is not split
+  FusedFinalize fz;
+  fz.colscale = stats + K;
+  fz.colshift = center_w ? stats + 2 * K : nullptr;
+  fz.rowa = (transpose && has_missing) ? impute : nullptr;
+  fz.rowscale = transpose ? scale : nullptr;
+  fz.rowshift = transpose ? center_w : nullptr;
+  fz.out = out;
+  fz.ldo = ldo;
+  bool fused = false;
+  rc = launch_geno_mma(store, M, Kd, m_limit, kd_limit, has_missing, (transpose && has_missing) ? 1 : 0, image1,
+                       two ? image2 : nullptr, K, P, N, acc0, (transpose && has_missing) ? acc1 : nullptr, 0, stream,
+                       &fz, &fused);
+  if (rc || fused) return rc;
+  return lmdec_finalize(acc0, fz.rowa ? acc1 : nullptr, m_limit, K, fz.colscale, fz.rowa, fz.rowscale, fz.rowshift,
+                        fz.colshift, out, ldo, stream);
+}
+
+int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, double* r, int* flag, void* stream) {
+  if (K < 1 || K > 128) return fail("lmdec_chol_whiten: K out of range (1..128)");
+  const size_t smem = (size_t)(2 * K * K + K) * sizeof(double);
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(chol_whiten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    attr_set = true;
+  }
+  chol_whiten_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(G, K, rank_tol, r_inv, r, flag);
+  return check_launch("lmdec_chol_whiten");
+}
+
+// ---- CUDA-event timing of the dominant kernel (bench.py's roofline): events are recorded on the launching stream
+void lmdec_kernel_timing(int on) {
+  for (auto& e : g_mma_events) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  g_mma_events.clear();
+  g_mma_timing = on != 0;
+}
+int lmdec_kernel_timing_read(double* total_ms, int64_t* launches) {
+  double tot = 0;
+  for (auto& e : g_mma_events) {
+    cudaEventSynchronize(e.second);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e.first, e.second);
+    tot += ms;
+  }
+  *total_ms = tot;
+  *launches = (int64_t)g_mma_events.size();
+  return 0;
 }
 
 }  // extern "C"

@@ -164,3 +164,16 @@ def sqdiff(a: torch.Tensor, b: torch.Tensor, s: torch.Tensor = None) -> torch.Te
     _capi.check(lib.lmdec_sqdiff(_capi.ptr(a), a.stride(0), _capi.ptr(b), b.stride(0), _capi.ptr(sc), a.shape[0],
                                  a.shape[1], _capi.ptr(out), _capi.ptr(work), _capi.stream_ptr()), "lmdec_sqdiff")
     return out
+
+
+def chol_whiten(G: torch.Tensor, rank_tol: float = 1e-12):
+    """Device K x K Cholesky whitening: returns (r_inv, r, flag) all on the device (flag int32[1])."""
+    lib = _capi.load()
+    K = G.shape[0]
+    G = G.contiguous()
+    r_inv = torch.empty((K, K), dtype=F64, device=G.device)
+    r = torch.empty((K, K), dtype=F64, device=G.device)
+    flag = torch.empty(1, dtype=torch.int32, device=G.device)
+    _capi.check(lib.lmdec_chol_whiten(_capi.ptr(G), K, float(rank_tol), _capi.ptr(r_inv), _capi.ptr(r),
+                                      _capi.ptr(flag), _capi.stream_ptr()), "lmdec_chol_whiten")
+    return r_inv, r, flag

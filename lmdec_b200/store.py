@@ -266,73 +266,70 @@ class GenotypeOperator:
         return op
 
     # ------------------------------------------------------------------ buffers
-    def _buffers(self, tag, Kd, M, K, two_images, two_outs):
+    def _buffers(self, K):
         P = self.planes
         N = _round16(K * P)
         if N > 128:
             raise ValueError(f"k + buffer = {K} with {P} planes needs N = {N} > 128 tensor-core columns; "
                              "lower `planes` or k + buffer")
-        key = (tag, K, P)
+        key = (K, P)
         b = self._buf.get(key)
         if b is None:
-            dev = self.store.device
-            nbytes = self.store.lib.lmdec_image_bytes(Kd, N)
+            st, dev = self.store, self.store.device
+            lib = st.lib
+            miss = self.has_missing
+            nb_dot, nb_tdot = lib.lmdec_image_bytes(st.p, N), lib.lmdec_image_bytes(st.n, N)
             b = {
                 "N": N,
-                "im1": torch.empty(nbytes, dtype=torch.int8, device=dev),
-                "im2": torch.empty(nbytes, dtype=torch.int8, device=dev) if two_images else None,
-                "out0": torch.empty((M, K), dtype=torch.int64, device=dev),
-                "out1": torch.empty((M, K), dtype=torch.int64, device=dev) if two_outs else None,
-                "amax": torch.empty(K, dtype=F64, device=dev),
-                "amax2": torch.empty(K, dtype=F64, device=dev),
+                "work": torch.empty(lib.lmdec_apply_work_doubles(K), dtype=F64, device=dev),
+                "im1": torch.empty(max(nb_dot, nb_tdot), dtype=torch.int8, device=dev),
+                "im2": torch.empty(nb_dot, dtype=torch.int8, device=dev) if miss else None,
+                "acc0": torch.empty((max(st.n, st.p), K), dtype=torch.int64, device=dev),
+                "acc1": torch.empty((st.p, K), dtype=torch.int64, device=dev) if miss else None,
             }
             self._buf[key] = b
         return b
 
-    def _mult(self, b, two):
-        s = torch.maximum(b["amax"], b["amax2"]) if two else b["amax"]
-        # |q1| <= 2^(8P-2); one bit less when the second image (q2 - 3 q1, |.| <= 3 |q1|) is produced
-        lim = float(2.0 ** (8 * self.planes - (3 if two else 2)))
-        # a zero column quantises to zero with any multiplier; inf/NaN columns poison the result on purpose
-        return torch.where(s > 0, lim / s, torch.ones_like(s))
+    def _center_w(self):
+        if self.mean is None:
+            return None
+        if getattr(self, "_cw", None) is None:
+            self._cw = (self.mean if self.inv_std is None else self.mean * self.inv_std).contiguous()
+        return self._cw
 
     # ------------------------------------------------------------------ the two products (torch tensors in/out)
+    def _apply(self, b_in: torch.Tensor, transpose: bool) -> torch.Tensor:
+        st, lib = self.store, self.store.lib
+        K = b_in.shape[1]
+        buf = self._buffers(K)
+        m = self.rows
+        if transpose:
+            store, M, Kd, m_lim, kd_lim = st.v_store, st.p, st.n, st.p, m
+        else:
+            store, M, Kd, m_lim, kd_lim = st.s_store, st.n, st.p, m, st.p
+        out = torch.empty((m_lim, K), dtype=F64, device=st.device)
+        if m == 0:
+            return out.zero_() if transpose else out
+        miss = self.has_missing
+        with _timed("tdot" if transpose else "dot"):
+            _capi.check(lib.lmdec_operator_apply(
+                _capi.ptr(store), M, Kd, m_lim, kd_lim, int(miss), int(transpose), _capi.ptr(b_in), b_in.stride(0),
+                K, self.planes, _capi.ptr(self.inv_std), _capi.ptr(self.impute_mean) if miss else None,
+                _capi.ptr(self._center_w()), _capi.ptr(buf["work"]), _capi.ptr(buf["im1"]), _capi.ptr(buf["im2"]),
+                _capi.ptr(buf["acc0"]), _capi.ptr(buf["acc1"]), _capi.ptr(out), K, _capi.stream_ptr()),
+                "lmdec_operator_apply")
+        return out
+
     def dot_t(self, t: torch.Tensor) -> torch.Tensor:
         """x[n_local, K] = A t  for t [p, K] float64 on the device."""
         squeeze = t.ndim == 1
         if squeeze:
             t = t[:, None]
-        st, lib = self.store, self.store.lib
-        if t.shape[0] != st.p:
+        if t.shape[0] != self.store.p:
             raise ValueError("shapes {} and {} not aligned".format(self.shape, tuple(t.shape)))
-        t = t.contiguous()
-        K = t.shape[1]
-        miss = self.has_missing
-        b = self._buffers("dot", st.p, st.n, K, miss, False)
-        sp = _capi.stream_ptr()
-        d, mu = self.inv_std, self.impute_mean
-        _capi.check(lib.lmdec_colabsmax(_capi.ptr(t), K, st.p, K, _capi.ptr(d), _capi.ptr(mu) if miss else None,
-                                        _capi.ptr(b["amax"]), _capi.ptr(b["amax2"]), sp), "colabsmax")
-        mult = self._mult(b, miss)
-        _capi.check(lib.lmdec_quantize_planes(_capi.ptr(t), K, st.p, st.p, K, self.planes, b["N"], _capi.ptr(mult),
-                                              _capi.ptr(d), _capi.ptr(mu) if miss else None, _capi.ptr(b["im1"]),
-                                              _capi.ptr(b["im2"]) if miss else None, sp), "quantize")
-        m = self.rows
-        x = torch.empty((m, K), dtype=F64, device=st.device)
-        if m == 0:
-            return x[:, 0] if squeeze else x
-        with _timed("dot"):
-            _capi.check(lib.lmdec_geno_matmul(_capi.ptr(st.s_store), st.n, st.p, m, st.p, int(miss), 0,
-                                              _capi.ptr(b["im1"]), _capi.ptr(b["im2"]) if miss else None, K,
-                                              self.planes, b["N"], _capi.ptr(b["out0"]), None, 0, sp),
-                        "geno_matmul (A.dot)")
-        colscale = 1.0 / mult
-        colshift = None
-        if self.mean is not None:
-            w = self.mean if d is None else self.mean * d
-            colshift = -(w @ t)
-        _capi.check(lib.lmdec_finalize(_capi.ptr(b["out0"]), None, m, K, _capi.ptr(colscale), None, None, None,
-                                       _capi.ptr(colshift), _capi.ptr(x), K, sp), "finalize")
+        if t.stride(1) != 1 or t.dtype != F64:
+            t = t.to(F64).contiguous()
+        x = self._apply(t, False)
         return x[:, 0] if squeeze else x
 
     def tdot_t(self, y: torch.Tensor) -> torch.Tensor:
@@ -340,40 +337,14 @@ class GenotypeOperator:
         squeeze = y.ndim == 1
         if squeeze:
             y = y[:, None]
-        st, lib = self.store, self.store.lib
-        m = self.rows
-        if y.shape[0] != m:
+        if y.shape[0] != self.rows:
             raise ValueError("shapes {} and {} not aligned".format(self.shape[::-1], tuple(y.shape)))
-        y = y.contiguous()
-        K = y.shape[1]
-        miss = self.has_missing
-        b = self._buffers("tdot", st.n, st.p, K, False, miss)
-        sp = _capi.stream_ptr()
-        w = torch.empty((st.p, K), dtype=F64, device=st.device)
-        if m == 0:
-            w.zero_()
-        else:
-            _capi.check(lib.lmdec_colabsmax(_capi.ptr(y), K, m, K, None, None, _capi.ptr(b["amax"]), None, sp))
-            mult = self._mult(b, False)
-            _capi.check(lib.lmdec_quantize_planes(_capi.ptr(y), K, st.n, m, K, self.planes, b["N"], _capi.ptr(mult),
-                                                  None, None, _capi.ptr(b["im1"]), None, sp), "quantize")
-            with _timed("tdot"):
-                _capi.check(lib.lmdec_geno_matmul(_capi.ptr(st.v_store), st.p, st.n, st.p, m, int(miss),
-                                                  1 if miss else 0, _capi.ptr(b["im1"]), None, K, self.planes, b["N"],
-                                                  _capi.ptr(b["out0"]), _capi.ptr(b["out1"]) if miss else None, 0, sp),
-                            "geno_matmul (A.T.dot)")
-            colscale = 1.0 / mult
-            d, mu = self.inv_std, self.impute_mean
-            rowshift = colshift = None
-            if self.mean is not None:
-                rowshift = -(self.mean if d is None else self.mean * d)
-                colshift = y.sum(0)
-            _capi.check(lib.lmdec_finalize(_capi.ptr(b["out0"]), _capi.ptr(b["out1"]) if miss else None, st.p, K,
-                                           _capi.ptr(colscale), _capi.ptr(mu) if miss else None, _capi.ptr(d),
-                                           _capi.ptr(rowshift), _capi.ptr(colshift), _capi.ptr(w), K, sp), "finalize")
-        if st.group is not None:
+        if y.stride(1) != 1 or y.dtype != F64:
+            y = y.to(F64).contiguous()
+        w = self._apply(y, True)
+        if self.store.group is not None:
             import torch.distributed as dist
-            dist.all_reduce(w, group=st.group)
+            dist.all_reduce(w, group=self.store.group)
         return w[:, 0] if squeeze else w
 
     # ------------------------------------------------------------------ materialisation (tests / small inputs)
