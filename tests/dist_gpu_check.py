@@ -1,0 +1,72 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/dist_gpu_check.py
+
+Every rank holds a block of rows of the same global genotype matrix; the row-sharded PowerMethod / SBPM must reproduce
+the single-GPU result on the full matrix (rank 0 computes it) and the CPU oracle.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import oracle, structured_genotypes  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from lmdec_b200 import PowerMethod
+    from lmdec_b200.decomp import make_snp_array
+
+    n, p, k, buffer = 1537, 4000, 6, 6
+    g = structured_genotypes(n, p, miss=0.04, seed=21)
+    bounds = np.linspace(0, n, world + 1).astype(int)
+    bounds[1:-1] = bounds[1:-1] // 256 * 256          # shard starts on store-chunk boundaries is NOT required; any split
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    x0 = np.random.default_rng(42).standard_normal((n, k + buffer))
+    kw = dict(k=k, buffer=buffer, tol=[1e-7, 1e-9], scoring_method=["q-vals", "v-subspace"], sub_svd_start=False,
+              lmbd=0, max_iter=40)
+
+    op = make_snp_array(g[lo:hi], group=dist.group.WORLD, n_global=n, row_offset=lo)
+    assert op.shape == (n, p)
+    pm = PowerMethod(**kw)
+    U, S, V = pm.svd(op, x0=x0[lo:hi], verbose=False)
+    u_parts = [None] * world
+    dist.all_gather_object(u_parts, np.asarray(U))
+    ok = True
+    if rank == 0:
+        U_all = np.concatenate(u_parts, axis=0)
+        op1 = make_snp_array(g)
+        pm1 = PowerMethod(**kw)
+        U1, S1, V1 = pm1.svd(op1, x0=x0, verbose=False)
+        Ur, Sr, Vr = oracle.PowerMethod(**kw).svd(oracle.make_snp_array(g), x0=x0)
+        S, V, S1, V1, U1 = np.asarray(S), np.asarray(V), np.asarray(S1), np.asarray(V1), np.asarray(U1)
+        checks = {
+            "iters equal": pm.num_iter == pm1.num_iter,
+            "S vs single GPU": np.allclose(S, S1, rtol=1e-6),
+            "S vs oracle": np.allclose(S, Sr, rtol=1e-4),
+            "U vs single GPU": oracle.subspace_dist(U_all, U1, S1) <= 1e-5,
+            "V vs single GPU": oracle.subspace_dist(V.T, V1.T, S1) <= 1e-5,
+            "U vs oracle": oracle.subspace_dist(U_all, Ur, Sr) <= 1e-4,
+            "V vs oracle": oracle.subspace_dist(V.T, Vr.T, Sr) <= 1e-4,
+        }
+        for name, good in checks.items():
+            print(f"[dist_gpu_check world={world}] {name}: {'ok' if good else 'FAIL'}")
+            ok = ok and bool(good)
+        print(f"[dist_gpu_check world={world}] iterations {pm.num_iter}, S = {np.round(S, 5)}")
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
