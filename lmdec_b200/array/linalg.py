@@ -89,9 +89,46 @@ def orthonormalize(x: torch.Tensor, group=None, seed: int = 0, gram_fn=None):
     return q, r_total
 
 
-def _orthonormalize_device(x: torch.Tensor, group=None):
-    """CholeskyQR2 with both K x K factorizations on the device and ONE device->host copy (r and the health flags).
-    Returns None when the iterate is not numerically full rank / finite: the caller then takes the host path."""
+_SIDE = {}
+
+
+def _side_stream(device):
+    st = _SIDE.get(device)
+    if st is None:
+        st = _SIDE[device] = (torch.cuda.Stream(device=device), torch.empty(128 * 128 + 8, dtype=F64).pin_memory())
+    return st
+
+
+class _PendingQR:
+    """Device half of CholeskyQR2 already enqueued; ``finish()`` makes the single device->host copy (r + health).
+
+    The copy runs on a side stream that waits only for the orthonormalisation (an event recorded right behind it), so
+    work queued on the main stream afterwards -- the products of the coming step -- does not delay it."""
+
+    def __init__(self, q, packed, K):
+        self.q, self._packed, self._K = q, packed, K
+        self._ev = torch.cuda.Event()
+        self._ev.record()
+
+    def finish(self):
+        """r [K,K] on the host, or None when the iterate was not numerically full rank / finite."""
+        K = self._K
+        side, pinned = _side_stream(self._packed.device)
+        side.wait_event(self._ev)
+        n = self._packed.numel()
+        with torch.cuda.stream(side):
+            pinned[:n].copy_(self._packed, non_blocking=True)
+        self._packed.record_stream(side)
+        side.synchronize()
+        host = pinned[:n].numpy().copy()
+        if host[K * K] != 0 or host[K * K + 1] != 0 or not (host[K * K + 2] < 1e-2):
+            return None
+        return host[:K * K].reshape(K, K)
+
+
+def orthonormalize_begin(x: torch.Tensor, group=None) -> _PendingQR:
+    """Enqueue CholeskyQR2 entirely on the device (both K x K factorizations included) and return without syncing, so
+    the caller can queue the next products behind it before asking for r."""
     K = x.shape[1]
     G1 = _allreduce(gram(x), group)
     ri1, r1, f1 = chol_whiten(G1)
@@ -101,10 +138,14 @@ def _orthonormalize_device(x: torch.Tensor, group=None):
     q = q1 @ ri2
     r = r2 @ r1
     dev2 = (G2 - torch.eye(K, dtype=F64, device=x.device)).abs().max().reshape(1)
-    host = torch.cat([r.reshape(-1), f1.to(F64), f2.to(F64), dev2]).cpu().numpy()
-    if host[K * K] != 0 or host[K * K + 1] != 0 or not (host[K * K + 2] < 1e-2):
-        return None
-    return q, host[:K * K].reshape(K, K)
+    packed = torch.cat([r.reshape(-1), f1.to(F64), f2.to(F64), dev2])
+    return _PendingQR(q, packed, K)
+
+
+def _orthonormalize_device(x: torch.Tensor, group=None):
+    pend = orthonormalize_begin(x, group)
+    r = pend.finish()
+    return None if r is None else (pend.q, r)
 
 
 def tsqr_svd(x: torch.Tensor, group=None):

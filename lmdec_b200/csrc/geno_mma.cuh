@@ -36,6 +36,9 @@ constexpr uint32_t kARingCol0 = 256;       // TMEM A ring: columns [256, 512); a
 constexpr int kMaxBStages = 4;
 constexpr int kMaxTileStages = 8;
 constexpr uint32_t kTileBytes = 8192;
+// mbarrier slots (8 bytes each) in one shared array, addressed by 32-bit shared-window addresses
+constexpr int kBarFullT = 0, kBarEmptyT = 8, kBarFullA = 16, kBarEmptyA = 20, kBarFullB = 24, kBarEmptyB = 28,
+              kBarAccFull = 32, kBarAccEmpty = 34, kNumBars = 36;
 
 // out[m,k] = (acc0 + rowa[m]*acc1) * colscale[k] * rowscale[m] + rowshift[m] * colshift[k]   (NULL = absent / 1)
 struct FusedFinalize {
@@ -87,6 +90,12 @@ __device__ __forceinline__ void decode16(uint32_t r, uint32_t* v, uint32_t* m) {
   }
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
 template <bool kMiss>
 __device__ __forceinline__ void produce_chunk(const uint4 (&raw)[2], uint32_t a_stage_addr, int half) {
   // this thread's 32 bytes = K-blocks 4*half .. 4*half+3 of the chunk; raw[i] = 64 codes = 2 K-blocks
@@ -108,8 +117,8 @@ __device__ __forceinline__ void produce_chunk(const uint4 (&raw)[2], uint32_t a_
 // Epilogue of one warp (one TMEM lane quarter, thread = output row).  Accumulator column n = k*P + plane, so the P
 // planes of 8 consecutive outputs are 8*P consecutive columns: everything stays in registers, indices are compile-time.
 template <int P>
-__device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t tbase, uint64_t* acc_full,
-                                              uint64_t* acc_empty, int warp, int lane, int acc_sets, uint32_t acc_w) {
+__device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t tbase, uint32_t acc_full,
+                                              uint32_t acc_empty, int warp, int lane, int acc_sets, uint32_t acc_w) {
   const int q = warp & 3;  // TMEM lane quarter this warp may touch
   const int row = q * 32 + lane;
   const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
@@ -121,7 +130,7 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
     const int mt = w % p.m_tiles;
     const uint32_t set = tile_no % acc_sets, set_phase = (tile_no / acc_sets) & 1;
     const uint32_t acc0 = lane_addr + (set * 2) * acc_w, acc1 = acc0 + acc_w;
-    mbar_wait(&acc_full[set], set_phase);
+    mbar_wait_a(acc_full + 8 * set, set_phase);
     tc_fence_after_sync();
     const long long m = (long long)mt * 128 + row;
     const bool live = m < p.m_limit;
@@ -147,7 +156,7 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
         // all TMEM reads of this tile are done: hand the accumulator set back to the issuers
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[set]);
+        if (lane == 0) mbar_arrive_a(acc_empty + 8 * set);
       }
       // undo the decode's byte scaling (exact: the sums are multiples of 64 / 128)
 #pragma unroll
@@ -204,11 +213,13 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
 
 __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full_t[kMaxTileStages], empty_t[kMaxTileStages];  // packed tiles (smem ring)
-  __shared__ uint64_t full_a[4], empty_a[4];                            // decoded A (TMEM ring)
-  __shared__ uint64_t full_b[kMaxBStages], empty_b[kMaxBStages];        // B image (smem ring)
-  __shared__ uint64_t acc_full[2], acc_empty[2];                        // accumulator sets
+  __shared__ uint64_t bars[kNumBars];  // see the kBar* offsets: all rings' full / empty barriers
   __shared__ uint32_t tmem_base_s;
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t full_t = bar0 + 8 * kBarFullT, empty_t = bar0 + 8 * kBarEmptyT;   // packed tiles (smem ring)
+  const uint32_t full_a = bar0 + 8 * kBarFullA, empty_a = bar0 + 8 * kBarEmptyA;   // decoded A (TMEM ring)
+  const uint32_t full_b = bar0 + 8 * kBarFullB, empty_b = bar0 + 8 * kBarEmptyB;   // B image (smem ring)
+  const uint32_t acc_full = bar0 + 8 * kBarAccFull, acc_empty = bar0 + 8 * kBarAccEmpty;  // accumulator sets
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N;
@@ -216,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   const uint32_t stage_bytes = img_bytes * p.n_img;
   uint8_t* smem_t = smem;                                              // tile ring
   uint8_t* smem_b = smem + (size_t)p.tile_stages * kTileBytes;         // B ring
+  const uint32_t smem_t_a = smem_u32(smem_t), smem_b_a = smem_u32(smem_b);
   const int a_stages = p.has_missing ? 2 : 4;
   const uint32_t a_stage_cols = p.has_missing ? 128 : 64;
   const int acc_sets = N <= 64 ? 2 : 1;
@@ -224,20 +236,20 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 32) {
     for (int i = 0; i < kMaxTileStages; ++i) {
-      mbar_init(&full_t[i], 1);
-      mbar_init(&empty_t[i], kProducerWarps);
+      mbar_init(&bars[kBarFullT + i], 1);
+      mbar_init(&bars[kBarEmptyT + i], kProducerWarps);
     }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&full_a[i], kProducerWarps);
-      mbar_init(&empty_a[i], 2);
+      mbar_init(&bars[kBarFullA + i], kProducerWarps);
+      mbar_init(&bars[kBarEmptyA + i], 2);
     }
     for (int i = 0; i < kMaxBStages; ++i) {
-      mbar_init(&full_b[i], 1);
-      mbar_init(&empty_b[i], 2);
+      mbar_init(&bars[kBarFullB + i], 1);
+      mbar_init(&bars[kBarEmptyB + i], 2);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 2);
-      mbar_init(&acc_empty[i], kEpilogueWarps);
+      mbar_init(&bars[kBarAccFull + i], 2);
+      mbar_init(&bars[kBarAccEmpty + i], kEpilogueWarps);
     }
     mbar_fence_init();
   }
@@ -261,12 +273,12 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       const int c0 = sp * chunks_per_split;
       const int c1 = min(c0 + chunks_per_split, p.n_chunks);
       for (int c = c0; c < c1; ++c) {
-        mbar_wait(&full_t[t_stage], t_phase);
-        const uint8_t* src = smem_t + (size_t)t_stage * kTileBytes + my_off;
+        mbar_wait_a(full_t + 8 * t_stage, t_phase);
+        const uint32_t src = smem_t_a + t_stage * kTileBytes + my_off;
         uint4 raw[2];
-        raw[0] = *reinterpret_cast<const uint4*>(src);
-        raw[1] = *reinterpret_cast<const uint4*>(src + 2048);
-        mbar_wait(&empty_a[a_stage], a_phase ^ 1);
+        raw[0] = lds128(src);
+        raw[1] = lds128(src + 2048);
+        mbar_wait_a(empty_a + 8 * a_stage, a_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t a_addr = lane_addr + kARingCol0 + a_stage * a_stage_cols;
         if (p.has_missing)
@@ -277,8 +289,8 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&full_a[a_stage]);
-          mbar_arrive(&empty_t[t_stage]);  // raw[] is consumed: the tile slot can be refilled
+          mbar_arrive_a(full_a + 8 * a_stage);
+          mbar_arrive_a(empty_t + 8 * t_stage);  // raw[] is consumed: the tile slot can be refilled
         }
         if (++a_stage == (uint32_t)a_stages) {
           a_stage = 0;
@@ -300,10 +312,10 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
         const int c1 = min(c0 + chunks_per_split, p.n_chunks);
         const uint8_t* tile0 = p.store + ((size_t)mt * p.store_kc) * kTileBytes;
         for (int c = c0; c < c1; ++c) {
-          mbar_wait(&empty_t[t_stage], t_phase ^ 1);
-          mbar_arrive_expect_tx(&full_t[t_stage], kTileBytes);
-          bulk_g2s(smem_t + (size_t)t_stage * kTileBytes, tile0 + (size_t)c * kTileBytes, kTileBytes,
-                   &full_t[t_stage]);
+          mbar_wait_a(empty_t + 8 * t_stage, t_phase ^ 1);
+          mbar_arrive_expect_tx_a(full_t + 8 * t_stage, kTileBytes);
+          bulk_g2s_a(smem_t_a + t_stage * kTileBytes, tile0 + (size_t)c * kTileBytes, kTileBytes,
+                     full_t + 8 * t_stage);
           if (++t_stage == (uint32_t)p.tile_stages) {
             t_stage = 0;
             t_phase ^= 1;
@@ -320,11 +332,12 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
         const int c0 = sp * chunks_per_split;
         const int c1 = min(c0 + chunks_per_split, p.n_chunks);
         for (int c = c0; c < c1; ++c) {
-          mbar_wait(&empty_b[b_stage], b_phase ^ 1);
-          uint8_t* dst = smem_b + (size_t)b_stage * stage_bytes;
-          mbar_arrive_expect_tx(&full_b[b_stage], stage_bytes);
-          bulk_g2s(dst, p.image1 + (size_t)c * img_bytes, img_bytes, &full_b[b_stage]);
-          if (p.n_img == 2) bulk_g2s(dst + img_bytes, p.image2 + (size_t)c * img_bytes, img_bytes, &full_b[b_stage]);
+          mbar_wait_a(empty_b + 8 * b_stage, b_phase ^ 1);
+          const uint32_t dst = smem_b_a + b_stage * stage_bytes;
+          mbar_arrive_expect_tx_a(full_b + 8 * b_stage, stage_bytes);
+          bulk_g2s_a(dst, p.image1 + (size_t)c * img_bytes, img_bytes, full_b + 8 * b_stage);
+          if (p.n_img == 2)
+            bulk_g2s_a(dst + img_bytes, p.image2 + (size_t)c * img_bytes, img_bytes, full_b + 8 * b_stage);
           if (++b_stage == (uint32_t)p.b_stages) {
             b_stage = 0;
             b_phase ^= 1;
@@ -344,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       const uint32_t plane = p.has_missing ? (uint32_t)me : 0u;
       const uint32_t img = (p.has_missing && p.n_img == 2) ? (uint32_t)me : 0u;
       // descriptor of the B ring base; stage / image / K-block offsets are added to its 16-byte address field
-      const uint64_t bdesc_ring = make_smem_desc(smem_u32(smem_b), lbo, 128) + (uint64_t)((img * img_bytes) >> 4);
+      const uint64_t bdesc_ring = make_smem_desc(smem_b_a, lbo, 128) + (uint64_t)((img * img_bytes) >> 4);
       const uint32_t a_ring = tbase + kARingCol0 + plane * 64;
       const uint32_t kb_step = (uint32_t)(2 * N);  // one K-block of the image, in 16-byte units
       uint32_t a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
@@ -355,12 +368,12 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
         const int c1 = min(c0 + chunks_per_split, p.n_chunks);
         const uint32_t set = tile_no % acc_sets, set_phase = (tile_no / acc_sets) & 1;
         const uint32_t d_addr = tbase + (set * 2 + me) * acc_w;
-        mbar_wait(&acc_empty[set], set_phase ^ 1);
+        mbar_wait_a(acc_empty + 8 * set, set_phase ^ 1);
         tc_fence_after_sync();
         uint32_t accumulate = 0;
         for (int c = c0; c < c1; ++c) {
-          mbar_wait(&full_a[a_stage], a_phase);
-          mbar_wait(&full_b[b_stage], b_phase);
+          mbar_wait_a(full_a + 8 * a_stage, a_phase);
+          mbar_wait_a(full_b + 8 * b_stage, b_phase);
           tc_fence_after_sync();
           const uint32_t a_addr = a_ring + a_stage * a_stage_cols;
           const uint64_t bdesc0 = bdesc_ring + (uint64_t)((b_stage * stage_bytes) >> 4);
@@ -375,8 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
               for (int j = 1; j < kKbPerChunk / 2; ++j)
                 umma_ts_i8(d_addr, a_addr + (2 * j + me) * 8, bdesc0 + (2 * j + me) * kb_step, idesc, 1u);
             }
-            umma_commit(&empty_a[a_stage]);
-            umma_commit(&empty_b[b_stage]);
+            umma_commit_a(empty_a + 8 * a_stage);
+            umma_commit_a(empty_b + 8 * b_stage);
           }
           __syncwarp();
           accumulate = 1;
@@ -389,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
             b_phase ^= 1;
           }
         }
-        if (elect_one()) umma_commit(&acc_full[set]);
+        if (elect_one()) umma_commit_a(acc_full + 8 * set);
         __syncwarp();
       }
     }

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 from tqdm import tqdm
 
-from ..array.linalg import orthonormalize, tsqr_svd
+from ..array.linalg import orthonormalize, orthonormalize_begin, tsqr_svd
 from ..array.matrix_ops import subspace_to_V
 from ..array.metrics import _rmse_from_products, q_value_converge, subspace_dist
 from ..array.operators import as_operator
@@ -168,6 +168,7 @@ class PowerMethod(_IterAlgo):
         self.compute = True
         self.scale, self.center, self.std_dist = scale, center, std_dist
         self.scaled_array = None
+        self.speculate = True
         self._cache = {}
 
     def project(self, x, onto, scale_center_x: bool = True):
@@ -175,10 +176,26 @@ class PowerMethod(_IterAlgo):
 
     # ------------------------------------------------------------------ per-iterate products
     def _state(self, x: torch.Tensor) -> dict:
-        """q, r of the iterate (CholeskyQR2) and, lazily, t = A^T q and the next iterate A t / factor."""
+        """q, r of the iterate (CholeskyQR2) and, lazily, t = A^T q and the next iterate A t / factor.
+
+        With ``speculate`` (default) the two products of the coming step are queued on the device right behind the
+        orthonormalisation, BEFORE the host asks for r: the K x K SVD, the q-vals check and the Python bookkeeping
+        then run while the GPU works, instead of the GPU idling behind them.  The only cost is one unused step when the
+        iterate turns out to be converged."""
         st = self._cache
         if st.get("x") is not x:
-            q, r = orthonormalize(x, _group_of(self.array))
+            group = _group_of(self.array)
+            K = x.shape[1]
+            if x.is_cuda and K <= 128:
+                pend = orthonormalize_begin(x, group)
+                st = self._cache = {"x": x, "q": pend.q}
+                if self.speculate:
+                    self._next(st)
+                r = pend.finish()
+                if r is not None:
+                    st["r"] = r
+                    return st
+            q, r = orthonormalize(x, group)      # rank-revealing host path (also raises LinAlgError on NaN/Inf)
             st = self._cache = {"x": x, "q": q, "r": r}
         return st
 
@@ -325,6 +342,7 @@ class _vPowerMethod(PowerMethod):
         self.v_start = as_tensor(v_start)
         self.k, self.buffer, self.full_svd = k, buffer, full_svd
         self.scale = self.center = self.std_dist = None
+        self.speculate = True
         self._cache = {}
 
     def _initialization(self, data, **kwargs):
