@@ -13,7 +13,18 @@ from .transform import acc_format_svd
 
 
 def q_value_converge(si, sj, scale: bool = True, norm: float = 2) -> float:
-    """|| si - sj ||_norm, scaled by the mean norm of the two (metrics.py:219-235)."""
+    """|| si - sj ||_norm, scaled by the mean norm of the two (metrics.py:219-235).
+
+    k-vectors that are already on the host (the drivers get S from the host-side K x K SVD) are reduced there; device
+    operands go through the warp-reduction kernel ``lmdec_qvals``."""
+    if isinstance(si, np.ndarray) and isinstance(sj, np.ndarray):
+        a, b = si.reshape(-1).astype(np.float64), sj.reshape(-1).astype(np.float64)
+        if a.shape != b.shape:
+            raise ValueError("Shapes of si and sj must match. Current {} != {}".format(a.shape, b.shape))
+        acc = np.linalg.norm(a - b, norm)
+        if scale:
+            acc /= (np.linalg.norm(a, norm) + np.linalg.norm(b, norm)) / 2
+        return float(acc)
     si_t, sj_t = as_tensor(si).reshape(-1), as_tensor(sj).reshape(-1)
     if si_t.shape != sj_t.shape:
         raise ValueError("Shapes of si and sj must match. Current {} != {}".format(tuple(si_t.shape),

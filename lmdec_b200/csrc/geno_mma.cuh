@@ -130,20 +130,21 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
     const int mt = w % p.m_tiles;
     const uint32_t set = tile_no % acc_sets, set_phase = (tile_no / acc_sets) & 1;
     const uint32_t acc0 = lane_addr + (set * 2) * acc_w, acc1 = acc0 + acc_w;
-    mbar_wait_a(acc_full + 8 * set, set_phase);
-    tc_fence_after_sync();
     const long long m = (long long)mt * 128 + row;
     const bool live = m < p.m_limit;
     long long* dst0 = p.out0 + m * K;
     long long* dst1 = p.out1 + m * K;
+    // per-row terms of the fused finalize are fetched BEFORE waiting for the accumulators (latency off the tile path)
     double row_a = 0.0, row_scale = 1.0, row_shift = 1.0;
     double* fdst = nullptr;
     if (p.fuse && live) {
-      if (p.fz.rowa) row_a = p.fz.rowa[m];
-      if (p.fz.rowscale) row_scale = p.fz.rowscale[m];
-      if (p.fz.rowshift) row_shift = p.fz.rowshift[m];
+      if (p.fz.rowa) row_a = __ldg(p.fz.rowa + m);
+      if (p.fz.rowscale) row_scale = __ldg(p.fz.rowscale + m);
+      if (p.fz.rowshift) row_shift = __ldg(p.fz.rowshift + m);
       fdst = p.fz.out + m * p.fz.ldo;
     }
+    mbar_wait_a(acc_full + 8 * set, set_phase);
+    tc_fence_after_sync();
     for (int g = 0; g < n_groups; ++g) {
       uint32_t r0[8 * P], r1[8 * P];
       const uint32_t col = (uint32_t)g * 8 * P;

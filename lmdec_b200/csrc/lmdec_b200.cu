@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) quantize_planes_kernel(const double* __re
   if (k < K) {
     const double mk = mult[k];
     // largest magnitude P balanced base-256 digits can hold: 127 * (256^P - 1) / 255
-    const double qmax = 127.0 * (ldexp(1.0, 8 * P) - 1.0) / 255.0;
+    const double qmax = floor(127.0 * (ldexp(1.0, 8 * P) - 1.0) / 255.0);
     const int64_t g0 = grp * 16;
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(256) quantize_planes_kernel(const double* __re
       if (g < kd_limit) {
         double x = B[g * ldb + k] * mk;
         if (row1) x *= row1[g];
-        const long long q1 = llrint(fmin(fmax(x, -qmax), qmax));
-        long long qv = q1;
+        const double q1d = rint(fmin(fmax(x, -qmax), qmax));   // |q| <= qmax < 2^31: 32-bit digit extraction
+        int qv = (int)q1d;
 #pragma unroll
         for (int pl = 0; pl < P; ++pl) {
           const int d = (int)(signed char)(qv & 255);
@@ -256,8 +256,8 @@ __global__ void __launch_bounds__(256) quantize_planes_kernel(const double* __re
         }
         if (image2) {
           // the product kernel multiplies RAW codes (3 at a missing entry) by image 1: image 2 carries q2 - 3 q1
-          qv = llrint(fmin(fmax(x * row2[g], -qmax), qmax)) - 3 * q1;
-          qv = qv > (long long)qmax ? (long long)qmax : (qv < -(long long)qmax ? -(long long)qmax : qv);
+          const double q2d = rint(fmin(fmax(x * row2[g], -qmax), qmax)) - 3.0 * q1d;
+          qv = (int)fmin(fmax(q2d, -qmax), qmax);
 #pragma unroll
           for (int pl = 0; pl < P; ++pl) {
             const int d = (int)(signed char)(qv & 255);
@@ -307,7 +307,7 @@ __global__ void colabsmax_kernel(const double* __restrict__ B, int64_t ldb, int6
 // Column statistics of a float64 operand in one pass: max |B r1|, max |B r1 r2| and sum_r w_r B_rk per column.
 // Deterministic: per-block partials (fixed row -> block map) reduced in block order by colstats_finish_kernel, which
 // also derives the fixed-point multiplier, its inverse and the rank-1 shift used by the finalize kernel.
-constexpr int kStatsMaxBlocks = 1184;
+constexpr int kStatsMaxBlocks = 592;
 __global__ void __launch_bounds__(256) colstats_partial_kernel(const double* __restrict__ B, int64_t ldb,
                                                                int64_t kd_limit, int K, const double* __restrict__ row1,
                                                                const double* __restrict__ row2,
@@ -317,14 +317,27 @@ __global__ void __launch_bounds__(256) colstats_partial_kernel(const double* __r
   const int k = threadIdx.x % K, ry = threadIdx.x / K, rpb = blockDim.x / K;
   double m1 = 0.0, m2 = 0.0, ws = 0.0;
   if (ry < rpb) {
-    for (int64_t r = (int64_t)blockIdx.x * rpb + ry; r < kd_limit; r += (int64_t)gridDim.x * rpb) {
-      const double b = B[r * ldb + k];
-      double v = fabs(b);
-      if (row1) v *= fabs(row1[r]);
-      if (v != v) v = INFINITY;  // NaN poisons the scale: the Gram check on the host side raises LinAlgError
-      m1 = fmax(m1, v);
-      if (row2) m2 = fmax(m2, v * fabs(row2[r]));
-      if (use_w) ws += (w ? w[r] : 1.0) * b;
+    const int64_t stride = (int64_t)gridDim.x * rpb;
+    constexpr int U = 8;  // independent loads in flight per thread
+    for (int64_t r0 = (int64_t)blockIdx.x * rpb + ry; r0 < kd_limit; r0 += stride * U) {
+      double b[U], a1[U], a2[U], ww[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + u * stride;
+        const bool in = r < kd_limit;
+        b[u] = in ? B[r * ldb + k] : 0.0;
+        a1[u] = (in && row1) ? row1[r] : 1.0;
+        a2[u] = (in && row2) ? row2[r] : 0.0;
+        ww[u] = (in && w) ? w[r] : 1.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double v = fabs(b[u]) * fabs(a1[u]);
+        if (v != v) v = INFINITY;  // NaN poisons the scale: the Gram check on the host side raises LinAlgError
+        m1 = fmax(m1, v);
+        m2 = fmax(m2, v * fabs(a2[u]));
+        if (use_w) ws += ww[u] * b[u];
+      }
     }
   }
   double* s1 = sm;

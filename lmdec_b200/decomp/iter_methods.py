@@ -25,7 +25,7 @@ from ..array.matrix_ops import subspace_to_V
 from ..array.metrics import _rmse_from_products, q_value_converge, subspace_dist
 from ..array.operators import as_operator
 from ..array.random import array_constant_partition, cumulative_partition
-from ..device import F64, DeviceArray, as_tensor
+from ..device import F64, DeviceArray, LazyDeviceArray, as_tensor
 from .init_methods import rnormal_start, sub_svd_init, sym_mat_mult_start
 from .utils import PowerMethodSummary
 
@@ -279,10 +279,17 @@ class PowerMethod(_IterAlgo):
         u_r, s, vh = np.linalg.svd(r, full_matrices=False)   # tsqr(x, compute_svd=True): matrix_ops.py:72
         k = self.k
         dev = x.device
-        u_rk = torch.as_tensor(np.ascontiguousarray(u_r[:, :k]), device=dev)
-        U_k = DeviceArray(q @ u_rk)
+        u_rk_np = np.ascontiguousarray(u_r[:, :k])
+        _dev_cache = {}
+
+        def u_rk():           # uploaded at most once, and only if somebody needs it
+            if "u" not in _dev_cache:
+                _dev_cache["u"] = torch.as_tensor(u_rk_np, device=dev)
+            return _dev_cache["u"]
+
+        U_k = LazyDeviceArray(lambda: q @ u_rk(), (x.shape[0], u_rk_np.shape[1]))
         S_np = np.sqrt(s)[:k]
-        S_k = DeviceArray(torch.as_tensor(S_np, device=dev))
+        S_k = LazyDeviceArray(lambda: torch.as_tensor(S_np, device=dev), S_np.shape)
         full_v = any(m in self.scoring_method for m in ["rmse", "v-subspace"])
         if full_v:
             # subspace_to_V (matrix_ops.py:89-99): left singular vectors of A^T x = t r; t is reused by the step
@@ -290,7 +297,8 @@ class PowerMethod(_IterAlgo):
             v, _, _ = tsqr_svd(w)
             V_k = DeviceArray(v.T[:k, :])
         else:
-            V_k = DeviceArray(torch.as_tensor(np.ascontiguousarray(vh[:k, :]), device=dev))
+            vh_k = np.ascontiguousarray(vh[:k, :])
+            V_k = LazyDeviceArray(lambda: torch.as_tensor(vh_k, device=dev), vh_k.shape)
         self.history.iter["last_value"] = (U_k, S_k, V_k)
         acc_list = []
         for method in self.scoring_method:
@@ -304,7 +312,7 @@ class PowerMethod(_IterAlgo):
             elif method == "rmse":
                 # rmse_k(array, U_k, S_k**2, factor) (iter_methods.py:410): A A^T U_k = (A t) u_r, shared with the step
                 n, p = self.array.shape
-                aatu = self._next(st) @ u_rk
+                aatu = self._next(st) @ u_rk()
                 acc = _rmse_from_products(aatu, U_k.t, S_k.t ** 2, n, k, p, self.factor, _group_of(self.array))
             else:  # 'v-subspace'
                 try:

@@ -91,6 +91,33 @@ class DeviceArray:
         return f"DeviceArray(shape={self.shape}, dtype={self.t.dtype}, device={self.t.device})"
 
 
+class LazyDeviceArray(DeviceArray):
+    """DeviceArray whose tensor is produced on first use.
+
+    The iteration stores (U_k, S_k, V_k) of every iterate in ``history.iter['last_value']`` (reference
+    lmdec/decomp/iter_methods.py:399); materialising U_k = q U_R and uploading the K-sized host results each iteration
+    would put pageable host->device copies -- which synchronise the stream -- into the hot loop.  They are deferred
+    until somebody looks at them (finalisation, KeyboardInterrupt recovery, a user reading the history)."""
+
+    def __init__(self, make, shape):
+        self._make, self._t, self._shape = make, None, tuple(shape)
+
+    @property
+    def t(self):
+        if self._t is None:
+            self._t = self._make()
+            self._make = None
+        return self._t
+
+    @property
+    def shape(self):
+        return self._shape
+
+    @property
+    def ndim(self):
+        return len(self._shape)
+
+
 def as_tensor(x, device=None, dtype=F64) -> torch.Tensor:
     """Anything array-like -> CUDA tensor of ``dtype`` (no copy when already there)."""
     device = device or require_cuda()
