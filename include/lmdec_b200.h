@@ -132,11 +132,13 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
  *             contracts it with B]
  *   work      lmdec_apply_work_doubles(K) doubles;  image1/2, acc0/1: caller-owned scratch (lmdec_image_bytes(Kd, N)
  *             with N = 16*ceil(K*P/16);  int64 [m_limit, K])
+ * transpose_flags: bit 0 = transpose; bit 1 = the statistics and plane images of B left in work / image1/2 by the
+ * previous call are reused (several output row ranges of the same product, e.g. to pipeline an all-reduce).
  * Steps: column statistics of B (max for the fixed-point scale, weighted column sum for the rank-1 term), plane
  * quantisation, lmdec_geno_matmul, lmdec_finalize.  */
 int64_t lmdec_apply_work_doubles(int K);
 int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
-                         int has_missing, int transpose, const double* B, int64_t ldb, int K, int P,
+                         int has_missing, int transpose_flags, const double* B, int64_t ldb, int K, int P,
                          const double* scale, const double* impute, const double* center_w, double* work,
                          int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, double* out, int64_t ldo,
                          void* stream);
@@ -146,6 +148,10 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
  * rank_tol, or non-finite input): the host then takes its rank-revealing path.  The K x K step of CholeskyQR2, in
  * place of dask tsqr's stacked-R QR (lmdec/decomp/iter_methods.py:382).  */
 int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, double* r, int* flag, void* stream);
+
+/* Leave `n_sms` SMs out of the persistent product kernel's grid so that a collective (NCCL) launched on another stream
+ * can run concurrently with it; 0 (default) = use every SM.  Process-wide setting. */
+void lmdec_set_sm_reserve(int n_sms);
 
 /* CUDA-event timing of lmdec_geno_matmul's kernel on its launching stream (bench.py's roofline figure). */
 void lmdec_kernel_timing(int on);

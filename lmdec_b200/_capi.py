@@ -35,6 +35,7 @@ SIGNATURES = {
                                     _p, _p, _p, _i64, _p]),
     "lmdec_chol_whiten": (_i32, [_p, _i32, C.c_double, _p, _p, _p, _p]),
     "lmdec_kernel_timing": (None, [_i32]),
+    "lmdec_set_sm_reserve": (None, [_i32]),
     "lmdec_kernel_timing_read": (_i32, [_p, _p]),
     "lmdec_sqdiff": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p]),
 }

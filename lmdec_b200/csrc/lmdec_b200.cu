@@ -31,6 +31,7 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_mma_events;
 static bool g_mma_timing = false;
+static int g_sm_reserve = 0;  // SMs left free for concurrently running collectives (row-sharded runs)
 
 namespace lmdec {
 
@@ -729,7 +730,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
     const int max_s = p.n_chunks / 4 > 1 ? (p.n_chunks / 4 < 256 ? p.n_chunks / 4 : 256) : 1;
     long long best = -1;
     for (int s_ = min_splits > 1 ? min_splits : 1; s_ <= max_s; ++s_) {
-      const long long waves = cdiv((long long)p.m_tiles * s_, n_sm);
+      const long long waves = cdiv((long long)p.m_tiles * s_, n_sm - g_sm_reserve > 8 ? n_sm - g_sm_reserve : 8);
       const long long cost = waves * (cdiv(p.n_chunks, s_) + 6) + (s_ > 1 ? 2 : 0);
       if (best < 0 || cost < best) {
         best = cost;
@@ -773,7 +774,8 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
     if (mode == 1) cudaMemsetAsync(out1, 0, (size_t)m_limit * K * 8, st);
   }
   const int n_work = p.m_tiles * p.splits;
-  const int grid = n_work < n_sm ? n_work : n_sm;
+  const int sm_avail = n_sm - g_sm_reserve > 8 ? n_sm - g_sm_reserve : 8;
+  const int grid = n_work < sm_avail ? n_work : sm_avail;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (g_mma_timing) {
     cudaEventCreate(&ev0);
@@ -849,11 +851,13 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
 int64_t lmdec_apply_work_doubles(int K) { return (int64_t)5 * K + (int64_t)kStatsMaxBlocks * 3 * K; }
 
 int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
-                         int has_missing, int transpose, const double* B, int64_t ldb, int K, int P,
+                         int has_missing, int transpose_flags, const double* B, int64_t ldb, int K, int P,
                          const double* scale, const double* impute, const double* center_w, double* work,
                          int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, double* out, int64_t ldo,
                          void* stream) {
   if (K < 1 || K > 128 || P < 1 || P > 4) return fail("lmdec_operator_apply: bad K/P");
+  const int transpose = transpose_flags & 1;
+  const bool reuse_operand = (transpose_flags & 2) != 0;  // stats + plane images of B are already in work / image1/2
   const int N = (K * P + 15) / 16 * 16;
   if (N > 128) return fail("lmdec_operator_apply: K*P needs more than 128 tensor-core columns");
   if (has_missing && !impute) return fail("lmdec_operator_apply: has_missing needs the imputation vector");
@@ -870,17 +874,20 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
   if (blocks < 1) blocks = 1;
   const int threads = 256;
   const double lim = ldexp(1.0, 8 * P - (two ? 3 : 2));
+  int rc = 0;
+  if (!reuse_operand) {
   colstats_partial_kernel<<<(unsigned)blocks, threads, 3 * threads * sizeof(double), st>>>(
       B, ldb, kd_limit, K, transpose ? nullptr : scale, two ? impute : nullptr, transpose ? nullptr : center_w,
       center_w != nullptr, partial);
   colstats_finish_kernel<<<1, 1024, (size_t)(1024 / K) * 3 * K * sizeof(double), st>>>(partial, (int)blocks, K, lim,
                                                                                           -1.0, stats);
-  int rc = check_launch("lmdec_operator_apply (colstats)", 2);
+  rc = check_launch("lmdec_operator_apply (colstats)", 2);
   if (rc) return rc;
   // ---- int8 planes
   rc = lmdec_quantize_planes(B, ldb, Kd, kd_limit, K, P, N, stats, transpose ? nullptr : scale,
                              two ? impute : nullptr, image1, two ? image2 : nullptr, stream);
   if (rc) return rc;
+  }
   // ---- tensor-core product, with the diagonal / rank-1 terms fused into its epilogue when it is not split
   FusedFinalize fz;
   fz.colscale = stats + K;
@@ -912,6 +919,8 @@ int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, do
 }
 
 // ---- CUDA-event timing of the dominant kernel (bench.py's roofline): events are recorded on the launching stream
+void lmdec_set_sm_reserve(int n_sms) { g_sm_reserve = n_sms < 0 ? 0 : n_sms; }
+
 void lmdec_kernel_timing(int on) {
   for (auto& e : g_mma_events) {
     cudaEventDestroy(e.first);

@@ -17,6 +17,7 @@ The two big products run exactly (int64) on the tensor cores: the float64 operan
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 from typing import Optional
 
@@ -28,6 +29,8 @@ from .device import F64, DeviceArray, as_tensor, require_cuda
 
 _DTYPE_CODE = {torch.int8: 0, torch.uint8: 1, torch.float32: 2, torch.float64: 3}
 
+
+_REDUCE_DTYPE = {"f32": torch.float32, "f64": torch.float64}[__import__("os").environ.get("LMDEC_REDUCE_DTYPE", "f32")]
 
 # bench.py sets this to a list to time the dominant kernel with CUDA events on the launching stream
 KERNEL_EVENTS = None
@@ -298,7 +301,9 @@ class GenotypeOperator:
         return self._cw
 
     # ------------------------------------------------------------------ the two products (torch tensors in/out)
-    def _apply(self, b_in: torch.Tensor, transpose: bool) -> torch.Tensor:
+    def _apply(self, b_in: torch.Tensor, transpose: bool, out: torch.Tensor = None, m_range=None,
+               reuse_operand: bool = False) -> torch.Tensor:
+        """One lmdec_operator_apply call; `m_range` = (m0, m1) restricts the OUTPUT rows (m0 a multiple of 128)."""
         st, lib = self.store, self.store.lib
         K = b_in.shape[1]
         buf = self._buffers(K)
@@ -307,16 +312,30 @@ class GenotypeOperator:
             store, M, Kd, m_lim, kd_lim = st.v_store, st.p, st.n, st.p, m
         else:
             store, M, Kd, m_lim, kd_lim = st.s_store, st.n, st.p, m, st.p
-        out = torch.empty((m_lim, K), dtype=F64, device=st.device)
+        if out is None:
+            out = torch.empty((m_lim, K), dtype=F64, device=st.device)
         if m == 0:
             return out.zero_() if transpose else out
+        m0, m1 = (0, m_lim) if m_range is None else m_range
+        if m0 % 128 or not (0 <= m0 < m1 <= m_lim):
+            raise ValueError("bad output row range")
         miss = self.has_missing
+
+        def off(t, per_row_bytes=8):
+            return None if t is None else C.c_void_p(t.data_ptr() + m0 * per_row_bytes)
+
+        row_vec = transpose  # scale / impute / centre vectors are per OUTPUT row only for A^T y
+        store_ptr = C.c_void_p(store.data_ptr() + (m0 // 128) * ((Kd + 255) // 256) * 8192)
         with _timed("tdot" if transpose else "dot"):
             _capi.check(lib.lmdec_operator_apply(
-                _capi.ptr(store), M, Kd, m_lim, kd_lim, int(miss), int(transpose), _capi.ptr(b_in), b_in.stride(0),
-                K, self.planes, _capi.ptr(self.inv_std), _capi.ptr(self.impute_mean) if miss else None,
-                _capi.ptr(self._center_w()), _capi.ptr(buf["work"]), _capi.ptr(buf["im1"]), _capi.ptr(buf["im2"]),
-                _capi.ptr(buf["acc0"]), _capi.ptr(buf["acc1"]), _capi.ptr(out), K, _capi.stream_ptr()),
+                store_ptr, M - m0, Kd, m1 - m0, kd_lim, int(miss), int(transpose) | (2 if reuse_operand else 0),
+                _capi.ptr(b_in), b_in.stride(0),
+                K, self.planes,
+                off(self.inv_std) if row_vec else _capi.ptr(self.inv_std),
+                (off(self.impute_mean) if row_vec else _capi.ptr(self.impute_mean)) if miss else None,
+                off(self._center_w()) if row_vec else _capi.ptr(self._center_w()),
+                _capi.ptr(buf["work"]), _capi.ptr(buf["im1"]), _capi.ptr(buf["im2"]),
+                _capi.ptr(buf["acc0"]), _capi.ptr(buf["acc1"]), off(out, K * 8), K, _capi.stream_ptr()),
                 "lmdec_operator_apply")
         return out
 
@@ -341,11 +360,46 @@ class GenotypeOperator:
             raise ValueError("shapes {} and {} not aligned".format(self.shape[::-1], tuple(y.shape)))
         if y.stride(1) != 1 or y.dtype != F64:
             y = y.to(F64).contiguous()
-        w = self._apply(y, True)
-        if self.store.group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(w, group=self.store.group)
+        if self.store.group is None:
+            w = self._apply(y, True)
+        else:
+            w = self._tdot_sharded(y)
         return w[:, 0] if squeeze else w
+
+    def _tdot_sharded(self, y: torch.Tensor) -> torch.Tensor:
+        """A^T y over row-sharded samples: the p x K partial products are all-reduced over NCCL.  Transport dtype
+        `store.reduce_dtype` (float32 by default: its 24-bit mantissa is finer than the 22-bit fixed point the result is
+        quantised to on its next use).  `reduce_parts` > 1 splits the product into SNP ranges and launches each range's
+        all-reduce asynchronously so that it overlaps the tensor-core work of the next range; measured on 2 x B200 the
+        extra launches cost as much as the overlap wins (profiles/r01/multi_gpu_notes.txt), so the default is 1."""
+        import torch.distributed as dist
+        st = self.store
+        K = y.shape[1]
+        w = torch.empty((st.p, K), dtype=F64, device=st.device)
+        n_tiles = (st.p + 127) // 128
+        parts = max(1, min(int(getattr(st, "reduce_parts", 0) or __import__("os").environ.get("LMDEC_REDUCE_PARTS", "1")),
+                           n_tiles))
+        rdt = getattr(st, "reduce_dtype", None) or _REDUCE_DTYPE
+        bounds = [min(st.p, (n_tiles * i // parts) * 128) for i in range(parts)] + [st.p]
+        pending = []
+        reserve = int(__import__("os").environ.get("LMDEC_SM_RESERVE", "16"))
+        st.lib.lmdec_set_sm_reserve(reserve if parts > 1 else 0)   # leave SMs for the concurrent NCCL kernels
+        for i in range(parts):
+            m0, m1 = bounds[i], bounds[i + 1]
+            if m1 <= m0:
+                continue
+            self._apply(y, True, out=w, m_range=(m0, m1), reuse_operand=bool(pending))
+            seg = w[m0:m1]
+            buf = seg if rdt == F64 else seg.to(rdt)
+            if __import__("os").environ.get("LMDEC_DEBUG_SKIP_ALLREDUCE"):
+                continue
+            pending.append((dist.all_reduce(buf, group=st.group, async_op=True), seg, buf))
+        st.lib.lmdec_set_sm_reserve(0)
+        for work, seg, buf in pending:
+            work.wait()
+            if buf is not seg:
+                seg.copy_(buf)
+        return w
 
     # ------------------------------------------------------------------ materialisation (tests / small inputs)
     def to_dense(self) -> torch.Tensor:

@@ -234,3 +234,70 @@ def test_metrics_closed_forms(cuda):
     for sv in (0.0, 0.5, 1.0):
         got = rmse_k(eye, eye, np.full(N, sv))
         assert abs(got - oracle.rmse_k(eye, eye, np.full(N, sv))) < 1e-14
+
+
+def test_config0_powermethod_10k_x_50k_matches_oracle(cuda):
+    """BASELINE.json configs[0]: PowerMethod k=10 on synthetic 10k x 50k binomial genotypes, centre + scale.
+    The oracle (reference's CPU path restated) runs on the host cores with the same x0 and tolerance."""
+    from lmdec_b200 import PowerMethod
+    from lmdec_b200.decomp import make_snp_array
+    n, p, k, buffer = 10_000, 50_000, 10, 10
+    g = synth_genotypes(n, p, 0.0, seed=0, dtype=np.float32)
+    x0 = np.random.default_rng(42).standard_normal((n, k + buffer))
+    kw = dict(k=k, buffer=buffer, tol=1e-3, scoring_method="q-vals", sub_svd_start=False, lmbd=0, max_iter=12)
+    ref = oracle.PowerMethod(**kw)
+    Ur, Sr, Vr = ref.svd(oracle.make_snp_array(g, std_method="binom"), x0=x0)
+    op = make_snp_array(g, std_method="binom")
+    assert not op.has_missing
+    pm = PowerMethod(**kw)
+    U, S, V = pm.svd(op, x0=x0, verbose=False)
+    assert pm.num_iter == ref.num_iter
+    np.testing.assert_allclose(_np(S), Sr, rtol=S_RTOL)
+    assert oracle.subspace_dist(_np(U), Ur, Sr) <= SUBSPACE_TOL
+    assert oracle.subspace_dist(_np(V).T, Vr.T, Sr) <= SUBSPACE_TOL
+
+
+def test_full_size_properties_config1(cuda):
+    """configs[1] size (2,504 x 1,000,000, 5% missing): size-independent properties instead of an oracle run.
+    (a) decode round trip and count checksum, (b) adjointness <A t, y> = <t, A^T y>, (c) linearity,
+    (d) column means of the operator are zero (centring) on a column sample."""
+    import torch
+    from lmdec_b200.store import GenotypeOperator, GenotypeStore
+    n, p = 2504, 1_000_000
+    gen = torch.Generator(device=cuda).manual_seed(7)
+    maf = torch.rand(p, generator=gen, device=cuda) * 0.45 + 0.05
+    store = GenotypeStore(n, p, device=cuda)
+    checksum = torch.zeros(4, dtype=torch.int64, device=cuda)
+    keep = {}
+    for r0 in range(0, n, 256):
+        nb = min(256, n - r0)
+        g = (torch.rand((nb, p), generator=gen, device=cuda) < maf).to(torch.int8)
+        g += (torch.rand((nb, p), generator=gen, device=cuda) < maf).to(torch.int8)
+        g[torch.rand((nb, p), generator=gen, device=cuda) < 0.05] = -1
+        for c, v in enumerate((0, 1, 2, -1)):
+            checksum[c] += (g == v).sum()
+        if r0 in (0, 2304):
+            keep[r0] = g.clone()
+        store.pack_rows(g, r0)
+    store.finish()
+    cnt = store.code_counts()
+    assert torch.equal(cnt.sum(0), checksum)                      # checksum of checksums, bit exact
+    assert int(cnt.sum().item()) == n * p
+    dec = store.to_dense(rows=256)
+    assert torch.equal(dec, keep[0])                              # decode round trip, first panel
+    dec_t = store.to_dense(transpose=True, rows=128)              # SNP-major store, first 128 SNPs, all samples
+    assert torch.equal(dec_t[:, 2304:2504], keep[2304][:, :128].T.contiguous())
+    mean, std = store.moments("binom")
+    op = GenotypeOperator(store, mean, 1.0 / std)
+    K = 20
+    t = torch.randn((p, K), generator=gen, device=cuda, dtype=torch.float64)
+    y = torch.randn((n, K), generator=gen, device=cuda, dtype=torch.float64)
+    at, aty = op.dot_t(t), op.tdot_t(y)
+    lhs, rhs = (at * y).sum().item(), (t * aty).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), torch.linalg.norm(at).item() * torch.linalg.norm(y).item())
+    t2 = torch.randn((p, K), generator=gen, device=cuda, dtype=torch.float64)
+    lin = op.dot_t(t + 2.0 * t2) - (at + 2.0 * op.dot_t(t2))
+    assert torch.linalg.norm(lin).item() <= 1e-5 * torch.linalg.norm(at).item()
+    ones = torch.ones((n, 1), dtype=torch.float64, device=cuda)
+    col_sums = op.tdot_t(ones)[:, 0]                              # 1^T A = 0 for a centred, mean-imputed operator
+    assert col_sums.abs().max().item() <= 1e-4 * np.sqrt(n)
