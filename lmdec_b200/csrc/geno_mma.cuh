@@ -24,13 +24,17 @@
 
 namespace lmdec {
 
-constexpr int kProducerWarps = 8;
-constexpr int kTileLoaderWarp = 8;
-constexpr int kIssuerWarp0 = 9;
-constexpr int kEpilogueWarp0 = 11;
+#ifndef LMDEC_PRODUCER_WARPS
+#define LMDEC_PRODUCER_WARPS 8
+#endif
+constexpr int kProducerWarps = LMDEC_PRODUCER_WARPS;          // 8 or 16 (4 lane quarters x 2 or 4 K-block groups)
+constexpr int kKbPerProducer = 32 / kProducerWarps;           // K-blocks of a chunk decoded by one producer thread
+constexpr int kTileLoaderWarp = kProducerWarps;
+constexpr int kIssuerWarp0 = kProducerWarps + 1;
+constexpr int kEpilogueWarp0 = kProducerWarps + 3;            // 4 consecutive warps cover the 4 TMEM lane quarters
 constexpr int kEpilogueWarps = 4;
-constexpr int kBLoaderWarp = 15;
-constexpr int kThreads = 16 * 32;
+constexpr int kBLoaderWarp = kProducerWarps + 7;
+constexpr int kThreads = (kProducerWarps + 8) * 32;
 constexpr int kKbPerChunk = 8;             // 8 K-blocks of 32 = one 256-wide contraction chunk = one store tile
 constexpr uint32_t kARingCol0 = 256;       // TMEM A ring: columns [256, 512); accumulators: [0, 256)
 constexpr int kMaxBStages = 4;
@@ -97,17 +101,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 template <bool kMiss>
-__device__ __forceinline__ void produce_chunk(const uint4 (&raw)[2], uint32_t a_stage_addr, int half) {
-  // this thread's 32 bytes = K-blocks 4*half .. 4*half+3 of the chunk; raw[i] = 64 codes = 2 K-blocks
+__device__ __forceinline__ void produce_chunk(const uint4 (&raw)[kKbPerProducer / 2], uint32_t a_stage_addr, int part) {
+  // this thread's bytes = K-blocks kKbPerProducer*part .. +kKbPerProducer of the chunk; raw[i] = 64 codes = 2 K-blocks
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kKbPerProducer / 2; ++i) {
     const uint32_t regs[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       uint32_t v[8], m[8];
       decode16<kMiss>(regs[2 * j], v, m);
       decode16<kMiss>(regs[2 * j + 1], v + 4, m + 4);
-      const int kb = 4 * half + 2 * i + j;
+      const int kb = kKbPerProducer * part + 2 * i + j;
       tmem_st8(a_stage_addr + kb * 8, v);
       if (kMiss) tmem_st8(a_stage_addr + 64 + kb * 8, m);
     }
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
-    const uint32_t my_off = (uint32_t)(2 * half) * 2048 + (uint32_t)row * 16;
+    const uint32_t my_off = (uint32_t)((kKbPerProducer / 2) * half) * 2048 + (uint32_t)row * 16;
     uint32_t a_stage = 0, a_phase = 0, t_stage = 0, t_phase = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int sp = w / p.m_tiles;
@@ -276,9 +280,9 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       for (int c = c0; c < c1; ++c) {
         mbar_wait_a(full_t + 8 * t_stage, t_phase);
         const uint32_t src = smem_t_a + t_stage * kTileBytes + my_off;
-        uint4 raw[2];
-        raw[0] = lds128(src);
-        raw[1] = lds128(src + 2048);
+        uint4 raw[kKbPerProducer / 2];
+#pragma unroll
+        for (int i = 0; i < kKbPerProducer / 2; ++i) raw[i] = lds128(src + i * 2048);
         mbar_wait_a(empty_a + 8 * a_stage, a_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t a_addr = lane_addr + kARingCol0 + a_stage * a_stage_cols;
