@@ -274,6 +274,11 @@ def run_ours(args):
         avg_kernel_ms = mma_total_ms / max(mma_launches, 1)
         flops_launch = 2.0 * N_ROWS * N_COLS * K          # per GPU, per geno_mma launch (one of the two products)
         achieved = flops_launch / (avg_kernel_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01", "geno_mma_traffic.json")
+        if os.path.exists(tpath) and args.planes == 3:
+            with open(tpath) as f:
+                traffic = json.load(f)["dram_bytes_per_launch_mean"]   # ncu --set full, dram read + write, per launch
         t_tensor = flops_launch / (pk["tensor_tflops"] * 1e12)
         t_hbm = (N_ROWS * N_COLS / 4) / (pk["hbm_gbs"] * 1e9)
         line = {
@@ -288,7 +293,7 @@ def run_ours(args):
                     "api": "x = op.dot(op.T.dot(q)) with q, x in pinned host memory (GenotypeOperator from make_snp_array)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tensor_tflops"], "traffic": None,
+                         "frac": achieved / pk["tensor_tflops"], "traffic": traffic,
                          "kernel": "geno_mma_kernel (2 launches per step: A^T q and A t)",
                          "avg_launch_ms": avg_kernel_ms, "launches_timed": mma_launches,
                          "kernel_share_of_step": mma_total_ms / ms_total,
