@@ -120,15 +120,36 @@ __device__ __forceinline__ void produce_chunk(const uint4 (&raw)[kKbPerProducer 
 
 // Epilogue of one warp (one TMEM lane quarter, thread = output row).  Accumulator column n = k*P + plane, so the P
 // planes of 8 consecutive outputs are 8*P consecutive columns: everything stays in registers, indices are compile-time.
+// MODE 0: out0 = acc0 + acc1;  MODE 1: out0 = acc0 - 3 acc1 (value plane carried raw codes), out1 = acc1.
+// OUT  0: int64 store, 1: int64 atomicAdd (split-K), 2: finalized float64 (fz_col = colscale[K] | colshift[K] in smem).
+enum { kOutStore = 0, kOutAtomic = 1, kOutFused = 2 };
+
 template <int P>
+__device__ __forceinline__ double planes_to_double(const uint32_t* r) {
+  double a = (double)(int)r[P - 1];   // planes are int32 and the combination is < 2^53: exact in float64
+#pragma unroll
+  for (int pl = P - 2; pl >= 0; --pl) a = fma(a, 256.0, (double)(int)r[pl]);
+  return a;
+}
+template <int P>
+__device__ __forceinline__ long long planes_to_int64(const uint32_t* r) {
+  long long a = (long long)(int)r[P - 1];
+#pragma unroll
+  for (int pl = P - 2; pl >= 0; --pl) a = a * 256 + (long long)(int)r[pl];
+  return a;
+}
+
+template <int P, int MODE, int OUT>
 __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t tbase, uint32_t acc_full,
-                                              uint32_t acc_empty, int warp, int lane, int acc_sets, uint32_t acc_w) {
+                                              uint32_t acc_empty, int warp, int lane, int acc_sets, uint32_t acc_w,
+                                              const double* fz_col) {
   const int q = warp & 3;  // TMEM lane quarter this warp may touch
   const int row = q * 32 + lane;
   const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
   const int K = p.K;
   const int n_groups = (K + 7) / 8;
   const int n_work = p.m_tiles * p.splits;
+  const int shift1 = p.has_missing ? kMissShift : kValueShift;
   uint32_t tile_no = 0;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
     const int mt = w % p.m_tiles;
@@ -141,12 +162,13 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
     // per-row terms of the fused finalize are fetched BEFORE waiting for the accumulators (latency off the tile path)
     double row_a = 0.0, row_scale = 1.0, row_shift = 1.0;
     double* fdst = nullptr;
-    if (p.fuse && live) {
+    if (OUT == kOutFused && live) {
       if (p.fz.rowa) row_a = __ldg(p.fz.rowa + m);
       if (p.fz.rowscale) row_scale = __ldg(p.fz.rowscale + m);
       if (p.fz.rowshift) row_shift = __ldg(p.fz.rowshift + m);
       fdst = p.fz.out + m * p.fz.ldo;
     }
+    const double row_a3 = (row_a - 3.0) * row_scale;  // MODE 1: out = rs*(acc0 - 3 acc1) + rs*ra*acc1
     mbar_wait_a(acc_full + 8 * set, set_phase);
     tc_fence_after_sync();
     for (int g = 0; g < n_groups; ++g) {
@@ -163,48 +185,37 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
         __syncwarp();
         if (lane == 0) mbar_arrive_a(acc_empty + 8 * set);
       }
+      if (!live) continue;
       // undo the decode's byte scaling (exact: the sums are multiples of 64 / 128)
 #pragma unroll
       for (int i = 0; i < 8 * P; ++i) {
         const int a0 = (int)r0[i] >> kValueShift;
-        const int a1 = p.has_missing ? ((int)r1[i] >> kMissShift) : ((int)r1[i] >> kValueShift);
-        if (p.mode == 1) {
-          r0[i] = (uint32_t)(a0 - 3 * a1);  // value plane carried raw codes: code 3 at the missing entries
+        const int a1 = (int)r1[i] >> shift1;
+        if (MODE == 1) {
+          r0[i] = (uint32_t)(OUT == kOutFused ? a0 : a0 - 3 * a1);
           r1[i] = (uint32_t)a1;
         } else {
           r0[i] = (uint32_t)(a0 + a1);
         }
       }
-      if (live) {
+      const int k_hi = min(8, K - g * 8);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+      for (int kk = 0; kk < 8; ++kk) {
+        if (kk < k_hi) {
           const int k = g * 8 + kk;
-          if (k < K) {
-            long long acc = (long long)(int)r0[kk * P + P - 1];
-#pragma unroll
-            for (int pl = P - 2; pl >= 0; --pl) acc = acc * 256 + (long long)(int)r0[kk * P + pl];
-            if (p.fuse) {
-              double v = (double)acc;
-              if (p.mode == 1) {
-                long long am = (long long)(int)r1[kk * P + P - 1];
-#pragma unroll
-                for (int pl = P - 2; pl >= 0; --pl) am = am * 256 + (long long)(int)r1[kk * P + pl];
-                v += row_a * (double)am;
-              }
-              v *= __ldg(p.fz.colscale + k) * row_scale;
-              if (p.fz.colshift) v += row_shift * __ldg(p.fz.colshift + k);
-              fdst[k] = v;
-              continue;
-            }
-            if (p.use_atomics)
+          if (OUT == kOutFused) {
+            double v = planes_to_double<P>(r0 + kk * P) * row_scale;
+            if (MODE == 1) v = fma(planes_to_double<P>(r1 + kk * P), row_a3, v);
+            fdst[k] = fma(v, fz_col[k], row_shift * fz_col[128 + k]);
+          } else {
+            const long long acc = planes_to_int64<P>(r0 + kk * P);
+            if (OUT == kOutAtomic)
               atomicAdd(reinterpret_cast<unsigned long long*>(dst0 + k), (unsigned long long)acc);
             else
               dst0[k] = acc;
-            if (p.mode == 1) {
-              long long am = (long long)(int)r1[kk * P + P - 1];
-#pragma unroll
-              for (int pl = P - 2; pl >= 0; --pl) am = am * 256 + (long long)(int)r1[kk * P + pl];
-              if (p.use_atomics)
+            if (MODE == 1) {
+              const long long am = planes_to_int64<P>(r1 + kk * P);
+              if (OUT == kOutAtomic)
                 atomicAdd(reinterpret_cast<unsigned long long*>(dst1 + k), (unsigned long long)am);
               else
                 dst1[k] = am;
@@ -216,10 +227,29 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
   }
 }
 
+template <int P>
+__device__ __forceinline__ void epilogue_dispatch(const GenoMmaParams& p, uint32_t tbase, uint32_t acc_full,
+                                                  uint32_t acc_empty, int warp, int lane, int acc_sets, uint32_t acc_w,
+                                                  const double* fz_col) {
+#define LMDEC_EPI(MODE, OUT) \
+  epilogue_loop<P, MODE, OUT>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col)
+  if (p.mode == 1) {
+    if (p.fuse) LMDEC_EPI(1, kOutFused);
+    else if (p.use_atomics) LMDEC_EPI(1, kOutAtomic);
+    else LMDEC_EPI(1, kOutStore);
+  } else {
+    if (p.fuse) LMDEC_EPI(0, kOutFused);
+    else if (p.use_atomics) LMDEC_EPI(0, kOutAtomic);
+    else LMDEC_EPI(0, kOutStore);
+  }
+#undef LMDEC_EPI
+}
+
 __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[kNumBars];  // see the kBar* offsets: all rings' full / empty barriers
   __shared__ uint32_t tmem_base_s;
+  __shared__ double fz_col[256];       // fused finalize: colscale[k] at [k], colshift[k] at [128 + k]
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t full_t = bar0 + 8 * kBarFullT, empty_t = bar0 + 8 * kBarEmptyT;   // packed tiles (smem ring)
   const uint32_t full_a = bar0 + 8 * kBarFullA, empty_a = bar0 + 8 * kBarEmptyA;   // decoded A (TMEM ring)
@@ -239,6 +269,11 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   const uint32_t acc_w = N <= 64 ? 64 : 128;
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  if (p.fuse && tid >= 64 && tid < 64 + 128) {
+    const int k = tid - 64;
+    fz_col[k] = k < p.K ? p.fz.colscale[k] : 0.0;
+    fz_col[128 + k] = (k < p.K && p.fz.colshift) ? p.fz.colshift[k] : 0.0;
+  }
   if (tid == 32) {
     for (int i = 0; i < kMaxTileStages; ++i) {
       mbar_init(&bars[kBarFullT + i], 1);
@@ -414,10 +449,10 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   } else {
     // ------------------------------------------------------------------ epilogue (warps 11..14)
     switch (p.P) {
-      case 1: epilogue_loop<1>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w); break;
-      case 2: epilogue_loop<2>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w); break;
-      case 3: epilogue_loop<3>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w); break;
-      default: epilogue_loop<4>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w); break;
+      case 1: epilogue_dispatch<1>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col); break;
+      case 2: epilogue_dispatch<2>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col); break;
+      case 3: epilogue_dispatch<3>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col); break;
+      default: epilogue_dispatch<4>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col); break;
     }
   }
   tc_fence_before_sync();

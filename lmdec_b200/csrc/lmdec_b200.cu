@@ -752,7 +752,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
   }
   const size_t stage_bytes = (size_t)8 * N * 32 * p.n_img;
   const size_t scratch = 0;
-  const size_t budget = 225 * 1024;  // 227 KB per CTA minus static barriers and alignment slack
+  const size_t budget = 222 * 1024;  // 227 KB per CTA minus the static barriers / column constants (3 KB) and slack
   int tile_stages = kMaxTileStages, b_stages = 0;
   for (; tile_stages >= 2; tile_stages /= 2) {
     b_stages = (int)((budget - scratch - (size_t)tile_stages * kTileBytes) / stage_bytes);
@@ -765,7 +765,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
   const size_t smem = (size_t)tile_stages * kTileBytes + b_stages * stage_bytes + scratch;
   cudaStream_t st = (cudaStream_t)stream;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(geno_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(geno_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
     if (e != cudaSuccess) return fail("lmdec_geno_matmul: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
