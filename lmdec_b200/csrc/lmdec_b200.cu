@@ -231,15 +231,15 @@ __global__ void __launch_bounds__(256) quantize_planes_kernel(const double* __re
   if (idx >= n_groups * kq) return;
   const int k = (int)(idx % kq);
   const int64_t grp = idx / kq;               // grp = kb*2 + h
-  uint32_t o1[P][4], o2[P][4];
+  // q = round(x) for |x| < 2^31 is the low word of x + 1.5*2^52 (one DADD, round-to-nearest-even like rint)
+  constexpr double kMagic = 6755399441055744.0;
+  int q1[16], q2[16];
 #pragma unroll
-  for (int pl = 0; pl < P; ++pl)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o1[pl][j] = o2[pl][j] = 0;
+  for (int e = 0; e < 16; ++e) q1[e] = q2[e] = 0;
   if (k < K) {
     const double mk = mult[k];
     // largest magnitude P balanced base-256 digits can hold: 127 * (256^P - 1) / 255
-    const double qmax = floor(127.0 * (ldexp(1.0, 8 * P) - 1.0) / 255.0);
+    const int qmax = (int)(127.0 * (ldexp(1.0, 8 * P) - 1.0) / 255.0);
     const int64_t g0 = grp * 16;
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
@@ -247,34 +247,41 @@ __global__ void __launch_bounds__(256) quantize_planes_kernel(const double* __re
       if (g < kd_limit) {
         double x = B[g * ldb + k] * mk;
         if (row1) x *= row1[g];
-        const double q1d = rint(fmin(fmax(x, -qmax), qmax));   // |q| <= qmax < 2^31: 32-bit digit extraction
-        int qv = (int)q1d;
-#pragma unroll
-        for (int pl = 0; pl < P; ++pl) {
-          const int d = (int)(signed char)(qv & 255);
-          qv = (qv - d) >> 8;
-          o1[pl][e >> 2] |= (uint32_t)(d & 255) << (8 * (e & 3));
-        }
+        x = fmin(fmax(x, (double)-qmax), (double)qmax);
+        q1[e] = __double2loint(x + kMagic);
         if (image2) {
           // the product kernel multiplies RAW codes (3 at a missing entry) by image 1: image 2 carries q2 - 3 q1
-          const double q2d = rint(fmin(fmax(x * row2[g], -qmax), qmax)) - 3.0 * q1d;
-          qv = (int)fmin(fmax(q2d, -qmax), qmax);
-#pragma unroll
-          for (int pl = 0; pl < P; ++pl) {
-            const int d = (int)(signed char)(qv & 255);
-            qv = (qv - d) >> 8;
-            o2[pl][e >> 2] |= (uint32_t)(d & 255) << (8 * (e & 3));
-          }
+          const double x2 = fmin(fmax(x * row2[g], (double)-qmax), (double)qmax);
+          q2[e] = min(max(__double2loint(x2 + kMagic) - 3 * q1[e], -qmax), qmax);
         }
       }
     }
   }
+  // balanced base-256 digits: the stored byte of plane pl is the low byte of q_pl, q_{pl+1} = (q_pl + 128) >> 8
   const size_t base = ((size_t)grp * N + (size_t)k * P) * 16;
 #pragma unroll
   for (int pl = 0; pl < P; ++pl) {
-    *reinterpret_cast<uint4*>(image1 + base + pl * 16) = make_uint4(o1[pl][0], o1[pl][1], o1[pl][2], o1[pl][3]);
-    if (image2)
-      *reinterpret_cast<uint4*>(image2 + base + pl * 16) = make_uint4(o2[pl][0], o2[pl][1], o2[pl][2], o2[pl][3]);
+    uint32_t w1[4], w2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t lo = __byte_perm((uint32_t)q1[4 * j], (uint32_t)q1[4 * j + 1], 0x0040);
+      const uint32_t hi = __byte_perm((uint32_t)q1[4 * j + 2], (uint32_t)q1[4 * j + 3], 0x0040);
+      w1[j] = __byte_perm(lo, hi, 0x5410);
+      if (image2) {
+        const uint32_t lo2 = __byte_perm((uint32_t)q2[4 * j], (uint32_t)q2[4 * j + 1], 0x0040);
+        const uint32_t hi2 = __byte_perm((uint32_t)q2[4 * j + 2], (uint32_t)q2[4 * j + 3], 0x0040);
+        w2[j] = __byte_perm(lo2, hi2, 0x5410);
+      }
+    }
+    *reinterpret_cast<uint4*>(image1 + base + pl * 16) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+    if (image2) *reinterpret_cast<uint4*>(image2 + base + pl * 16) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+    if (pl + 1 < P) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        q1[e] = (q1[e] + 128) >> 8;
+        q2[e] = (q2[e] + 128) >> 8;
+      }
+    }
   }
 }
 // columns [ (N/P)*P, N ) are not covered by the groups above when P does not divide N: zero them
