@@ -152,6 +152,8 @@ int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, do
 /* Leave `n_sms` SMs out of the persistent product kernel's grid so that a collective (NCCL) launched on another stream
  * can run concurrently with it; 0 (default) = use every SM.  Process-wide setting. */
 void lmdec_set_sm_reserve(int n_sms);
+/* 1 (default): long contractions process two 128-row tiles per staged operand chunk; 0: one tile (A/B comparison). */
+void lmdec_set_pair_mode(int on);
 
 /* CUDA-event timing of lmdec_geno_matmul's kernel on its launching stream (bench.py's roofline figure). */
 void lmdec_kernel_timing(int on);

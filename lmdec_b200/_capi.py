@@ -36,6 +36,7 @@ SIGNATURES = {
     "lmdec_chol_whiten": (_i32, [_p, _i32, C.c_double, _p, _p, _p, _p]),
     "lmdec_kernel_timing": (None, [_i32]),
     "lmdec_set_sm_reserve": (None, [_i32]),
+    "lmdec_set_pair_mode": (None, [_i32]),
     "lmdec_kernel_timing_read": (_i32, [_p, _p]),
     "lmdec_sqdiff": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p]),
 }
@@ -62,6 +63,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("LMDEC_PAIR_MODE") is not None:      # A/B switch for the two-tiles-per-operand-chunk schedule
+        lib.lmdec_set_pair_mode(int(os.environ["LMDEC_PAIR_MODE"]))
     _LIB = lib
     return lib
 

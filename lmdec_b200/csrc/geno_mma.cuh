@@ -73,6 +73,8 @@ struct GenoMmaParams {
   int b_stages;
   int tile_stages;
   int use_atomics;
+  int pair;                // 0: one m-tile per work item; 1/2/3: TWO m-tiles share every B stage (kPairM/E/T)
+  int m_units;             // work items per split: m_tiles, or ceil(m_tiles / 2) in pair mode
   int fuse;                // write the finalized float64 result from the epilogue (never with atomics)
   FusedFinalize fz;
 };
@@ -123,6 +125,11 @@ __device__ __forceinline__ void produce_chunk(const uint4 (&raw)[kKbPerProducer 
 // MODE 0: out0 = acc0 + acc1;  MODE 1: out0 = acc0 - 3 acc1 (value plane carried raw codes), out1 = acc1.
 // OUT  0: int64 store, 1: int64 atomicAdd (split-K), 2: finalized float64 (fz_col = colscale[K] | colshift[K] in smem).
 enum { kOutStore = 0, kOutAtomic = 1, kOutFused = 2 };
+// Pair modes.  The operand image is the dominant L2 -> SM traffic (every m-tile re-reads all of it); processing two
+// m-tiles against one staged chunk halves it.  M: missing data, issuer i runs plane i of both tiles (4 accumulators of
+// 64 columns); E: no missing data, issuer i takes K-blocks of parity i of both tiles (4 x 64); T: no missing data and
+// N > 64, issuer i owns tile i (2 accumulators of 128 columns).
+enum { kPairNone = 0, kPairM = 1, kPairE = 2, kPairT = 3 };
 
 template <int P>
 __device__ __forceinline__ double planes_to_double(const uint32_t* r) {
@@ -148,77 +155,88 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
   const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
   const int K = p.K;
   const int n_groups = (K + 7) / 8;
-  const int n_work = p.m_tiles * p.splits;
+  const int n_work = p.m_units * p.splits;
   const int shift1 = p.has_missing ? kMissShift : kValueShift;
+  const int tiles_per_item = p.pair ? 2 : 1;
   uint32_t tile_no = 0;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
-    const int mt = w % p.m_tiles;
-    const uint32_t set = tile_no % acc_sets, set_phase = (tile_no / acc_sets) & 1;
-    const uint32_t acc0 = lane_addr + (set * 2) * acc_w, acc1 = acc0 + acc_w;
-    const long long m = (long long)mt * 128 + row;
-    const bool live = m < p.m_limit;
-    long long* dst0 = p.out0 + m * K;
-    long long* dst1 = p.out1 + m * K;
-    // per-row terms of the fused finalize are fetched BEFORE waiting for the accumulators (latency off the tile path)
-    double row_a = 0.0, row_scale = 1.0, row_shift = 1.0;
-    double* fdst = nullptr;
-    if (OUT == kOutFused && live) {
-      if (p.fz.rowa) row_a = __ldg(p.fz.rowa + m);
-      if (p.fz.rowscale) row_scale = __ldg(p.fz.rowscale + m);
-      if (p.fz.rowshift) row_shift = __ldg(p.fz.rowshift + m);
-      fdst = p.fz.out + m * p.fz.ldo;
-    }
-    const double row_a3 = (row_a - 3.0) * row_scale;  // MODE 1: out = rs*(acc0 - 3 acc1) + rs*ra*acc1
+    const int unit = w % p.m_units;
+    // accumulator hand-shake: per accumulator set when single tiles alternate between two sets, one for a pair
+    const uint32_t set = p.pair ? 0u : tile_no % acc_sets;
+    const uint32_t set_phase = p.pair ? (tile_no & 1) : ((tile_no / acc_sets) & 1);
     mbar_wait_a(acc_full + 8 * set, set_phase);
     tc_fence_after_sync();
-    for (int g = 0; g < n_groups; ++g) {
-      uint32_t r0[8 * P], r1[8 * P];
-      const uint32_t col = (uint32_t)g * 8 * P;
-#pragma unroll
-      for (int i = 0; i < P; ++i) tmem_ld8p(acc0 + col + i * 8, r0 + 8 * i);
-#pragma unroll
-      for (int i = 0; i < P; ++i) tmem_ld8p(acc1 + col + i * 8, r1 + 8 * i);
-      tmem_wait_ld();
-      if (g == n_groups - 1) {
-        // all TMEM reads of this tile are done: hand the accumulator set back to the issuers
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_a(acc_empty + 8 * set);
+    for (int t = 0; t < tiles_per_item; ++t) {
+      const int mt = p.pair ? 2 * unit + t : unit;
+      const uint32_t slot = p.pair ? (uint32_t)t : set;
+      const uint32_t acc0 = lane_addr + (p.pair == kPairT ? slot : slot * 2) * acc_w, acc1 = acc0 + acc_w;
+      const long long m = (long long)mt * 128 + row;
+      const bool live = mt < p.m_tiles && m < p.m_limit;
+      long long* dst0 = p.out0 + m * K;
+      long long* dst1 = p.out1 + m * K;
+      double row_a = 0.0, row_scale = 1.0, row_shift = 1.0;
+      double* fdst = nullptr;
+      if (OUT == kOutFused && live) {
+        if (p.fz.rowa) row_a = __ldg(p.fz.rowa + m);
+        if (p.fz.rowscale) row_scale = __ldg(p.fz.rowscale + m);
+        if (p.fz.rowshift) row_shift = __ldg(p.fz.rowshift + m);
+        fdst = p.fz.out + m * p.fz.ldo;
       }
-      if (!live) continue;
-      // undo the decode's byte scaling (exact: the sums are multiples of 64 / 128)
+      const double row_a3 = (row_a - 3.0) * row_scale;  // MODE 1: out = rs*(acc0 - 3 acc1) + rs*ra*acc1
+      for (int g = 0; g < n_groups; ++g) {
+        uint32_t r0[8 * P], r1[8 * P];
+        const uint32_t col = (uint32_t)g * 8 * P;
 #pragma unroll
-      for (int i = 0; i < 8 * P; ++i) {
-        const int a0 = (int)r0[i] >> kValueShift;
-        const int a1 = (int)r1[i] >> shift1;
-        if (MODE == 1) {
-          r0[i] = (uint32_t)(OUT == kOutFused ? a0 : a0 - 3 * a1);
-          r1[i] = (uint32_t)a1;
+        for (int i = 0; i < P; ++i) tmem_ld8p(acc0 + col + i * 8, r0 + 8 * i);
+        if (p.pair == kPairT) {
+#pragma unroll
+          for (int i = 0; i < 8 * P; ++i) r1[i] = 0;  // one accumulator per tile
         } else {
-          r0[i] = (uint32_t)(a0 + a1);
-        }
-      }
-      const int k_hi = min(8, K - g * 8);
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        if (kk < k_hi) {
-          const int k = g * 8 + kk;
-          if (OUT == kOutFused) {
-            double v = planes_to_double<P>(r0 + kk * P) * row_scale;
-            if (MODE == 1) v = fma(planes_to_double<P>(r1 + kk * P), row_a3, v);
-            fdst[k] = fma(v, fz_col[k], row_shift * fz_col[128 + k]);
+          for (int i = 0; i < P; ++i) tmem_ld8p(acc1 + col + i * 8, r1 + 8 * i);
+        }
+        tmem_wait_ld();
+        if (g == n_groups - 1 && t == tiles_per_item - 1) {
+          // all TMEM reads of this work item are done: hand the accumulators back to the issuers
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(acc_empty + 8 * set);
+        }
+        if (!live) continue;
+        // undo the decode's byte scaling (exact: the sums are multiples of 64 / 128)
+#pragma unroll
+        for (int i = 0; i < 8 * P; ++i) {
+          const int a0 = (int)r0[i] >> kValueShift;
+          const int a1 = (int)r1[i] >> shift1;
+          if (MODE == 1) {
+            r0[i] = (uint32_t)(OUT == kOutFused ? a0 : a0 - 3 * a1);
+            r1[i] = (uint32_t)a1;
           } else {
-            const long long acc = planes_to_int64<P>(r0 + kk * P);
-            if (OUT == kOutAtomic)
-              atomicAdd(reinterpret_cast<unsigned long long*>(dst0 + k), (unsigned long long)acc);
-            else
-              dst0[k] = acc;
-            if (MODE == 1) {
-              const long long am = planes_to_int64<P>(r1 + kk * P);
+            r0[i] = (uint32_t)(a0 + a1);
+          }
+        }
+        const int k_hi = min(8, K - g * 8);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          if (kk < k_hi) {
+            const int k = g * 8 + kk;
+            if (OUT == kOutFused) {
+              double v = planes_to_double<P>(r0 + kk * P) * row_scale;
+              if (MODE == 1) v = fma(planes_to_double<P>(r1 + kk * P), row_a3, v);
+              fdst[k] = fma(v, fz_col[k], row_shift * fz_col[128 + k]);
+            } else {
+              const long long acc = planes_to_int64<P>(r0 + kk * P);
               if (OUT == kOutAtomic)
-                atomicAdd(reinterpret_cast<unsigned long long*>(dst1 + k), (unsigned long long)am);
+                atomicAdd(reinterpret_cast<unsigned long long*>(dst0 + k), (unsigned long long)acc);
               else
-                dst1[k] = am;
+                dst0[k] = acc;
+              if (MODE == 1) {
+                const long long am = planes_to_int64<P>(r1 + kk * P);
+                if (OUT == kOutAtomic)
+                  atomicAdd(reinterpret_cast<unsigned long long*>(dst1 + k), (unsigned long long)am);
+                else
+                  dst1[k] = am;
+              }
             }
           }
         }
@@ -281,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars[kBarFullA + i], kProducerWarps);
-      mbar_init(&bars[kBarEmptyA + i], 2);
+      mbar_init(&bars[kBarEmptyA + i], p.pair == kPairT ? 1 : 2);
     }
     for (int i = 0; i < kMaxBStages; ++i) {
       mbar_init(&bars[kBarFullB + i], 1);
@@ -298,8 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   tc_fence_after_sync();
   const uint32_t tbase = tmem_base_s;
 
-  const int n_work = p.m_tiles * p.splits;
+  const int n_work = p.m_units * p.splits;
   const int chunks_per_split = (p.n_chunks + p.splits - 1) / p.splits;
+  const int tiles_per_item = p.pair ? 2 : 1;
 
   if (warp < kProducerWarps) {
     // ------------------------------------------------------------------ producers
@@ -309,10 +328,11 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     const uint32_t my_off = (uint32_t)((kKbPerProducer / 2) * half) * 2048 + (uint32_t)row * 16;
     uint32_t a_stage = 0, a_phase = 0, t_stage = 0, t_phase = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int sp = w / p.m_tiles;
+      const int sp = w / p.m_units;
       const int c0 = sp * chunks_per_split;
       const int c1 = min(c0 + chunks_per_split, p.n_chunks);
-      for (int c = c0; c < c1; ++c) {
+      // in pair mode the tile stream alternates between the two m-tiles of the work item, chunk by chunk
+      for (int sc = (c1 - c0) * tiles_per_item; sc > 0; --sc) {
         mbar_wait_a(full_t + 8 * t_stage, t_phase);
         const uint32_t src = smem_t_a + t_stage * kTileBytes + my_off;
         uint4 raw[kKbPerProducer / 2];
@@ -347,18 +367,24 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     if (lane == 0) {
       uint32_t t_stage = 0, t_phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int mt = w % p.m_tiles, sp = w / p.m_tiles;
+        const int unit = w % p.m_units, sp = w / p.m_units;
         const int c0 = sp * chunks_per_split;
         const int c1 = min(c0 + chunks_per_split, p.n_chunks);
-        const uint8_t* tile0 = p.store + ((size_t)mt * p.store_kc) * kTileBytes;
+        // a pair whose second tile does not exist (odd m_tiles) streams the first tile twice; the epilogue drops it
+        const int mt0 = p.pair ? 2 * unit : unit;
+        const int mt1 = p.pair ? min(2 * unit + 1, p.m_tiles - 1) : unit;
+        const uint8_t* tile_a = p.store + ((size_t)mt0 * p.store_kc) * kTileBytes;
+        const uint8_t* tile_b = p.store + ((size_t)mt1 * p.store_kc) * kTileBytes;
         for (int c = c0; c < c1; ++c) {
-          mbar_wait_a(empty_t + 8 * t_stage, t_phase ^ 1);
-          mbar_arrive_expect_tx_a(full_t + 8 * t_stage, kTileBytes);
-          bulk_g2s_a(smem_t_a + t_stage * kTileBytes, tile0 + (size_t)c * kTileBytes, kTileBytes,
-                     full_t + 8 * t_stage);
-          if (++t_stage == (uint32_t)p.tile_stages) {
-            t_stage = 0;
-            t_phase ^= 1;
+          for (int t = 0; t < tiles_per_item; ++t) {
+            mbar_wait_a(empty_t + 8 * t_stage, t_phase ^ 1);
+            mbar_arrive_expect_tx_a(full_t + 8 * t_stage, kTileBytes);
+            bulk_g2s_a(smem_t_a + t_stage * kTileBytes, (t ? tile_b : tile_a) + (size_t)c * kTileBytes, kTileBytes,
+                       full_t + 8 * t_stage);
+            if (++t_stage == (uint32_t)p.tile_stages) {
+              t_stage = 0;
+              t_phase ^= 1;
+            }
           }
         }
       }
@@ -368,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     if (lane == 0) {
       uint32_t b_stage = 0, b_phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int sp = w / p.m_tiles;
+        const int sp = w / p.m_units;
         const int c0 = sp * chunks_per_split;
         const int c1 = min(c0 + chunks_per_split, p.n_chunks);
         for (int c = c0; c < c1; ++c) {
@@ -402,41 +428,54 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       const uint32_t kb_step = (uint32_t)(2 * N);  // one K-block of the image, in 16-byte units
       uint32_t a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       uint32_t tile_no = 0;
+      const bool all_kb = p.has_missing || p.pair == kPairT;  // this issuer runs all 8 K-blocks of a chunk (else parity me)
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
-        const int sp = w / p.m_tiles;
+        const int sp = w / p.m_units;
         const int c0 = sp * chunks_per_split;
         const int c1 = min(c0 + chunks_per_split, p.n_chunks);
-        const uint32_t set = tile_no % acc_sets, set_phase = (tile_no / acc_sets) & 1;
-        const uint32_t d_addr = tbase + (set * 2 + me) * acc_w;
+        const uint32_t set = p.pair ? 0u : tile_no % acc_sets;
+        const uint32_t set_phase = p.pair ? (tile_no & 1) : ((tile_no / acc_sets) & 1);
         mbar_wait_a(acc_empty + 8 * set, set_phase ^ 1);
         tc_fence_after_sync();
-        uint32_t accumulate = 0;
+        uint32_t accumulate[2] = {0, 0};
         for (int c = c0; c < c1; ++c) {
-          mbar_wait_a(full_a + 8 * a_stage, a_phase);
           mbar_wait_a(full_b + 8 * b_stage, b_phase);
-          tc_fence_after_sync();
-          const uint32_t a_addr = a_ring + a_stage * a_stage_cols;
           const uint64_t bdesc0 = bdesc_ring + (uint64_t)((b_stage * stage_bytes) >> 4);
-          if (elect_one()) {
-            if (p.has_missing) {
-              umma_ts_i8(d_addr, a_addr, bdesc0, idesc, accumulate);
 #pragma unroll
-              for (int j = 1; j < kKbPerChunk; ++j) umma_ts_i8(d_addr, a_addr + j * 8, bdesc0 + j * kb_step, idesc, 1u);
-            } else {
-              umma_ts_i8(d_addr, a_addr + me * 8, bdesc0 + me * kb_step, idesc, accumulate);
+          for (int t = 0; t < 2; ++t) {
+            if (t < tiles_per_item) {
+              const bool mine = p.pair != kPairT || t == me;
+              if (mine) {
+                mbar_wait_a(full_a + 8 * a_stage, a_phase);
+                tc_fence_after_sync();
+                const uint32_t slot = p.pair ? (uint32_t)t : set;
+                const uint32_t d_addr = tbase + (p.pair == kPairT ? slot : slot * 2 + me) * acc_w;
+                const uint32_t a_addr = a_ring + a_stage * a_stage_cols;
+                if (elect_one()) {
+                  if (all_kb) {
+                    umma_ts_i8(d_addr, a_addr, bdesc0, idesc, accumulate[t]);
 #pragma unroll
-              for (int j = 1; j < kKbPerChunk / 2; ++j)
-                umma_ts_i8(d_addr, a_addr + (2 * j + me) * 8, bdesc0 + (2 * j + me) * kb_step, idesc, 1u);
+                    for (int j = 1; j < kKbPerChunk; ++j)
+                      umma_ts_i8(d_addr, a_addr + j * 8, bdesc0 + j * kb_step, idesc, 1u);
+                  } else {
+                    umma_ts_i8(d_addr, a_addr + me * 8, bdesc0 + me * kb_step, idesc, accumulate[t]);
+#pragma unroll
+                    for (int j = 1; j < kKbPerChunk / 2; ++j)
+                      umma_ts_i8(d_addr, a_addr + (2 * j + me) * 8, bdesc0 + (2 * j + me) * kb_step, idesc, 1u);
+                  }
+                  umma_commit_a(empty_a + 8 * a_stage);
+                }
+                __syncwarp();
+                accumulate[t] = 1;
+              }
+              if (++a_stage == (uint32_t)a_stages) {
+                a_stage = 0;
+                a_phase ^= 1;
+              }
             }
-            umma_commit_a(empty_a + 8 * a_stage);
-            umma_commit_a(empty_b + 8 * b_stage);
           }
+          if (elect_one()) umma_commit_a(empty_b + 8 * b_stage);  // after every MMA that reads this B stage
           __syncwarp();
-          accumulate = 1;
-          if (++a_stage == (uint32_t)a_stages) {
-            a_stage = 0;
-            a_phase ^= 1;
-          }
           if (++b_stage == (uint32_t)p.b_stages) {
             b_stage = 0;
             b_phase ^= 1;

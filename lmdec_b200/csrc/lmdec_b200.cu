@@ -31,7 +31,8 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_mma_events;
 static bool g_mma_timing = false;
-static int g_sm_reserve = 0;  // SMs left free for concurrently running collectives (row-sharded runs)
+static int g_sm_reserve = 0;
+static int g_pair_mode = 1;   // lmdec_set_pair_mode: 0 disables the two-tiles-per-B-stage schedule (A/B tests)  // SMs left free for concurrently running collectives (row-sharded runs)
 
 namespace lmdec {
 
@@ -729,6 +730,15 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
   p.N = N;
   p.out0 = (long long*)out0;
   p.out1 = (long long*)out1;
+  // pair mode: two m-tiles share every staged chunk of the operand image (halves the dominant L2 -> SM traffic).  Only
+  // for long contractions (the accumulators are not double-buffered across work items) and when TMEM has room.
+  p.pair = kPairNone;
+  if (p.m_tiles >= 2 && p.n_chunks >= 64 && g_pair_mode) {
+    if (has_missing && N <= 64) p.pair = kPairM;
+    else if (!has_missing && N <= 64) p.pair = kPairE;
+    else if (!has_missing) p.pair = kPairT;
+  }
+  p.m_units = p.pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
   // split-K: minimise the makespan  ceil(work / SMs) * (chunks per split + per-item overhead)  over the split count;
   // the int32 accumulators cap a split at 256 chunks (value bytes are 64*code: 64 * 3 * 127 * 65536 < 2^31)
   int want = splits;
@@ -737,8 +747,8 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
     const int max_s = p.n_chunks / 4 > 1 ? (p.n_chunks / 4 < 256 ? p.n_chunks / 4 : 256) : 1;
     long long best = -1;
     for (int s_ = min_splits > 1 ? min_splits : 1; s_ <= max_s; ++s_) {
-      const long long waves = cdiv((long long)p.m_tiles * s_, n_sm - g_sm_reserve > 8 ? n_sm - g_sm_reserve : 8);
-      const long long cost = waves * (cdiv(p.n_chunks, s_) + 6) + (s_ > 1 ? 2 : 0);
+      const long long waves = cdiv((long long)p.m_units * s_, n_sm - g_sm_reserve > 8 ? n_sm - g_sm_reserve : 8);
+      const long long cost = waves * ((p.pair ? 2 : 1) * cdiv(p.n_chunks, s_) + 6) + (s_ > 1 ? 2 : 0);
       if (best < 0 || cost < best) {
         best = cost;
         want = s_;
@@ -780,7 +790,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
     cudaMemsetAsync(out0, 0, (size_t)m_limit * K * 8, st);
     if (mode == 1) cudaMemsetAsync(out1, 0, (size_t)m_limit * K * 8, st);
   }
-  const int n_work = p.m_tiles * p.splits;
+  const int n_work = p.m_units * p.splits;
   const int sm_avail = n_sm - g_sm_reserve > 8 ? n_sm - g_sm_reserve : 8;
   const int grid = n_work < sm_avail ? n_work : sm_avail;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -926,6 +936,8 @@ int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, do
 }
 
 // ---- CUDA-event timing of the dominant kernel (bench.py's roofline): events are recorded on the launching stream
+void lmdec_set_pair_mode(int on) { g_pair_mode = on != 0; }
+
 void lmdec_set_sm_reserve(int n_sms) { g_sm_reserve = n_sms < 0 ? 0 : n_sms; }
 
 void lmdec_kernel_timing(int on) {

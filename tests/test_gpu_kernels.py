@@ -78,6 +78,13 @@ def _quantize(torch, capi, lib, B, kd_limit, K, P, N, mult, row1=None, row2=None
     (260, 40000, 20, 3, 0.05, 0, 7),
     (1, 1, 1, 1, 0.0, 0, 1),
     (40000, 260, 30, 4, 0.02, 1, 0),
+    # long contractions: two m-tiles per staged operand chunk (pair modes M / E / T), odd tile counts, split and unsplit
+    (300, 20000, 20, 3, 0.05, 1, 0),
+    (300, 20000, 20, 3, 0.05, 1, 1),
+    (700, 17000, 20, 3, 0.0, 0, 0),
+    (640, 17000, 30, 3, 0.0, 0, 1),
+    (129, 33000, 20, 4, 0.0, 0, 3),
+    (256, 16384, 10, 2, 0.03, 0, 2),
 ])
 def test_geno_matmul_exact(cuda, M, Kd, K, P, miss, mode, splits):
     import torch
