@@ -221,8 +221,10 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
           if (kk < k_hi) {
             const int k = g * 8 + kk;
             if (OUT == kOutFused) {
-              double v = planes_to_double<P>(r0 + kk * P) * row_scale;
-              if (MODE == 1) v = fma(planes_to_double<P>(r1 + kk * P), row_a3, v);
+              // integer plane combine (ALU pipe) and ONE int64 -> float64 conversion per accumulator: the fp64 /
+              // conversion pipe is the scarce one in this epilogue (stall_math in profiles/r01)
+              double v = (double)planes_to_int64<P>(r0 + kk * P) * row_scale;
+              if (MODE == 1) v = fma((double)planes_to_int64<P>(r1 + kk * P), row_a3, v);
               fdst[k] = fma(v, fz_col[k], row_shift * fz_col[128 + k]);
             } else {
               const long long acc = planes_to_int64<P>(r0 + kk * P);
