@@ -107,32 +107,46 @@ def workload_config(n_gpus):
 # ---------------------------------------------------------------------------------------------------------------
 # this build
 # ---------------------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+class ClockSampler:
+    """nvidia-smi in loop mode (one process, a sample every 10 ms) with host timestamps; `summary(t0, t1)` keeps the
+    samples that fall inside the timed region (and reports how many did)."""
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.samples = []   # (host time, sm MHz, max MHz, [active reasons])
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "10"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                f = [x.strip() for x in out.split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for nm, v in zip(names, f[2:]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(nm)
+                reasons = [nm for nm, v in zip(self.NAMES, f[2:]) if v.lower().startswith("active")]
+                self.samples.append((time.time(), float(f[0]), float(f[1]), reasons))
             except Exception:
                 pass
-            time.sleep(0.1)
 
-    def summary(self):
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        used, where = (inside, "timed region") if len(inside) >= 2 else \
+            ([s for s in self.samples if s[0] >= t0 - 0.5], "timed region and the loaded phases around it")
+        reasons = sorted({r for s in used for r in s[3]})
+        return {"sm_mhz": float(np.median([s[1] for s in used])) if used else None,
+                "sm_max_mhz": used[0][2] if used else None, "reasons": reasons, "samples": len(used),
+                "samples_in_timed_region": len(inside), "window": where}
 
 
 def make_shard(torch, device, n, p, miss, seed):
@@ -201,7 +215,7 @@ def run_ours(args):
         x = one_step(x)
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    time.sleep(0.05)
     store_mod.KERNEL_EVENTS = []
     lib.lmdec_kernel_timing(1)
     launches0 = lib.lmdec_launch_count()
@@ -209,11 +223,13 @@ def run_ours(args):
     barrier()
     if args.profile_range:
         torch.cuda.profiler.start()      # ncu --profile-from-start off captures only the timed steps
+    t_region0 = time.time()
     e0.record()
     for _ in range(args.steps):
         x = one_step(x)
     e1.record()
     barrier()
+    t_region1 = time.time()
     if args.profile_range:
         torch.cuda.profiler.stop()
     ms_total = e0.elapsed_time(e1)
@@ -247,7 +263,7 @@ def run_ours(args):
         e2e_step()
     f1.record()
     barrier()
-    sampler.stop_flag = True
+    sampler.stop()
     e2e_ms_total = f0.elapsed_time(f1)
 
     times = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device=device)
@@ -286,7 +302,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int8 x int8 -> int32 tensor cores (exact), f64 small algebra",
             "data": "synthetic", "config": workload_config(world),
-            "clocks": sampler.summary(),
+            "clocks": sampler.summary(t_region0, t_region1),
             "e2e": {"value": flops_step / (e2e_ms_step * 1e-3) / 1e12, "unit": "TFLOP/s",
                     "h2d_bytes_per_step": N_ROWS * K * 8, "d2h_bytes_per_step": N_ROWS * K * 8,
                     "ms_per_step": e2e_ms_step,

@@ -133,14 +133,16 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
  *   work      lmdec_apply_work_doubles(K) doubles;  image1/2, acc0/1: caller-owned scratch (lmdec_image_bytes(Kd, N)
  *             with N = 16*ceil(K*P/16);  int64 [m_limit, K])
  * transpose_flags: bit 0 = transpose; bit 1 = the statistics and plane images of B left in work / image1/2 by the
- * previous call are reused (several output row ranges of the same product, e.g. to pipeline an all-reduce).
+ * previous call are reused (several output row ranges of the same product, e.g. to pipeline an all-reduce);
+ * bit 2 = B is float32 (else float64); bit 3 = out is float32 (else float64).  The p x K side of the iteration is
+ * carried in float32 (24-bit mantissa > the 22-bit fixed point it is quantised to), the n x K side in float64.
  * Steps: column statistics of B (max for the fixed-point scale, weighted column sum for the rank-1 term), plane
  * quantisation, lmdec_geno_matmul, lmdec_finalize.  */
 int64_t lmdec_apply_work_doubles(int K);
 int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
-                         int has_missing, int transpose_flags, const double* B, int64_t ldb, int K, int P,
+                         int has_missing, int transpose_flags, const void* B, int64_t ldb, int K, int P,
                          const double* scale, const double* impute, const double* center_w, double* work,
-                         int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, double* out, int64_t ldo,
+                         int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, void* out, int64_t ldo,
                          void* stream);
 
 /* K x K Cholesky whitening on the device (one block, float64): G = r^T r, r upper triangular, r_inv = r^-1.

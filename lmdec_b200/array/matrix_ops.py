@@ -29,7 +29,7 @@ def subspace_to_V(x, a, k=None, group=None):
     (matrix_ops.py:89-99).  Returns a [k, p] DeviceArray."""
     from .operators import as_operator
     a = as_operator(a)
-    x_t = _tdot(a, as_tensor(x))
+    x_t = _tdot(a, as_tensor(x)).to(F64)
     v, _, _ = tsqr_svd(x_t)          # a^T x is replicated on every rank: no collective
     v = v.T
     if k:

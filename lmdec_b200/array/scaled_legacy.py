@@ -239,8 +239,14 @@ class ScaledCenterArray:
             return x - (torch.outer(mu, s) if dx.ndim == 2 else mu * s)
         return x - mu @ dx
 
+    def _raw_tdot(self, x):
+        from ..store import GenotypeOperator
+        if isinstance(self._array, GenotypeOperator):
+            return self._array.tdot_t(x, out_dtype=F64)     # the legacy API is float64 end to end
+        return self._array.tdot_t(x)
+
     def _sym_t(self, x):
-        x_h = self._array.tdot_t(x)
+        x_h = self._raw_tdot(x)
         if self.center:
             x_h = self._center_x(x_h, x, transpose=True)
         if self.scale:
@@ -257,7 +263,7 @@ class ScaledCenterArray:
         d = self._moment()._scale_vector
         if not self._t_flag and self.scale:
             x = d[:, None] * x if x.ndim == 2 else d * x
-        y = self._array.tdot_t(x) if self._t_flag else self._array.dot_t(x)
+        y = self._raw_tdot(x) if self._t_flag else self._array.dot_t(x)
         if self.center:
             y = self._center_x(y, x, transpose=self._t_flag)
         if self._t_flag and self.scale:

@@ -51,8 +51,9 @@ struct FusedFinalize {
   const double* rowa;
   const double* rowscale;
   const double* rowshift;
-  double* out;
+  void* out;      // float64, or float32 when out_f32
   long long ldo;
+  int out_f32;
 };
 
 struct GenoMmaParams {
@@ -176,11 +177,13 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
       long long* dst1 = p.out1 + m * K;
       double row_a = 0.0, row_scale = 1.0, row_shift = 1.0;
       double* fdst = nullptr;
+      float* fdst32 = nullptr;
       if (OUT == kOutFused && live) {
         if (p.fz.rowa) row_a = __ldg(p.fz.rowa + m);
         if (p.fz.rowscale) row_scale = __ldg(p.fz.rowscale + m);
         if (p.fz.rowshift) row_shift = __ldg(p.fz.rowshift + m);
-        fdst = p.fz.out + m * p.fz.ldo;
+        fdst = (double*)p.fz.out + m * p.fz.ldo;
+        fdst32 = (float*)p.fz.out + m * p.fz.ldo;
       }
       const double row_a3 = (row_a - 3.0) * row_scale;  // MODE 1: out = rs*(acc0 - 3 acc1) + rs*ra*acc1
       for (int g = 0; g < n_groups; ++g) {
@@ -225,7 +228,11 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
               // conversion pipe is the scarce one in this epilogue (stall_math in profiles/r01)
               double v = (double)planes_to_int64<P>(r0 + kk * P) * row_scale;
               if (MODE == 1) v = fma((double)planes_to_int64<P>(r1 + kk * P), row_a3, v);
-              fdst[k] = fma(v, fz_col[k], row_shift * fz_col[128 + k]);
+              v = fma(v, fz_col[k], row_shift * fz_col[128 + k]);
+              if (p.fz.out_f32)
+                fdst32[k] = (float)v;
+              else
+                fdst[k] = v;
             } else {
               const long long acc = planes_to_int64<P>(r0 + kk * P);
               if (OUT == kOutAtomic)

@@ -219,8 +219,8 @@ __global__ void store_transpose_kernel(const uint8_t* __restrict__ src, int64_t 
 // writes the P plane units of image 1 (and of image 2).  Unit (kb, h, n) sits at ((kb*2 + h)*N + n)*16 bytes; byte e of
 // a unit is MMA contraction index 16h + e, which the producers' decode maps to genotype position
 // 16h + (e>>2) + 4*(e&3) of the K-block (geno_mma.cuh decode16).  Column n = k*P + plane.
-template <int P>
-__global__ void __launch_bounds__(256) quantize_planes_kernel(const double* __restrict__ B, int64_t ldb,
+template <int P, typename TB>
+__global__ void __launch_bounds__(256) quantize_planes_kernel(const TB* __restrict__ B, int64_t ldb,
                                                               int64_t kd_limit, int K, int N,
                                                               const double* __restrict__ mult,
                                                               const double* __restrict__ row1,
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256) quantize_planes_kernel(const double* __re
     for (int e = 0; e < 16; ++e) {
       const int64_t g = g0 + (e >> 2) + 4 * (e & 3);
       if (g < kd_limit) {
-        double x = B[g * ldb + k] * mk;
+        double x = (double)B[g * ldb + k] * mk;
         if (row1) x *= row1[g];
         x = fmin(fmax(x, (double)-qmax), (double)qmax);
         q1[e] = __double2loint(x + kMagic);
@@ -317,7 +317,8 @@ __global__ void colabsmax_kernel(const double* __restrict__ B, int64_t ldb, int6
 // Deterministic: per-block partials (fixed row -> block map) reduced in block order by colstats_finish_kernel, which
 // also derives the fixed-point multiplier, its inverse and the rank-1 shift used by the finalize kernel.
 constexpr int kStatsMaxBlocks = 592;
-__global__ void __launch_bounds__(256) colstats_partial_kernel(const double* __restrict__ B, int64_t ldb,
+template <typename TB>
+__global__ void __launch_bounds__(256) colstats_partial_kernel(const TB* __restrict__ B, int64_t ldb,
                                                                int64_t kd_limit, int K, const double* __restrict__ row1,
                                                                const double* __restrict__ row2,
                                                                const double* __restrict__ w, int use_w,
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(256) colstats_partial_kernel(const double* __r
       for (int u = 0; u < U; ++u) {
         const int64_t r = r0 + u * stride;
         const bool in = r < kd_limit;
-        b[u] = in ? B[r * ldb + k] : 0.0;
+        b[u] = in ? (double)B[r * ldb + k] : 0.0;
         a1[u] = (in && row1) ? row1[r] : 1.0;
         a2[u] = (in && row2) ? row2[r] : 0.0;
         ww[u] = (in && w) ? w[r] : 1.0;
@@ -405,10 +406,11 @@ __global__ void __launch_bounds__(1024) colstats_finish_kernel(const double* __r
   }
 }
 
+template <typename TO>
 __global__ void finalize_kernel(const long long* __restrict__ acc0, const long long* __restrict__ acc1, int64_t M, int K,
                                 const double* __restrict__ colscale, const double* __restrict__ rowa,
                                 const double* __restrict__ rowscale, const double* __restrict__ rowshift,
-                                const double* __restrict__ colshift, double* __restrict__ out, int64_t ldo) {
+                                const double* __restrict__ colshift, TO* __restrict__ out, int64_t ldo) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * K) return;
   const int64_t m = idx / K;
@@ -418,7 +420,7 @@ __global__ void finalize_kernel(const long long* __restrict__ acc0, const long l
   v *= colscale[k];
   if (rowscale) v *= rowscale[m];
   if (colshift) v += (rowshift ? rowshift[m] : 1.0) * colshift[k];
-  out[m * ldo + k] = v;
+  out[m * ldo + k] = (TO)v;
 }
 
 // ------------------------------------------------------------------------------------------------ fp64 reductions
@@ -656,9 +658,12 @@ int lmdec_code_counts(const uint8_t* store, int64_t M, int64_t Kd, int64_t kd_li
   return check_launch("lmdec_code_counts");
 }
 
-int lmdec_quantize_planes(const double* B, int64_t ldb, int64_t Kd, int64_t kd_limit, int K, int P, int N,
-                          const double* mult, const double* row1, const double* row2, int8_t* image1, int8_t* image2,
-                          void* stream) {
+}  // extern "C"
+
+template <typename TB>
+static int quantize_planes_t(const TB* B, int64_t ldb, int64_t Kd, int64_t kd_limit, int K, int P, int N,
+                             const double* mult, const double* row1, const double* row2, int8_t* image1,
+                             int8_t* image2, void* stream) {
   if (P < 1 || P > 4 || K < 1 || N % 16 || N < 16 || N > 128 || K * P > N)
     return fail("lmdec_quantize_planes: need 1<=P<=4, N%16==0, 16<=N<=128, K*P<=N");
   if (image2 && !row2) return fail("lmdec_quantize_planes: image2 needs row2");
@@ -667,16 +672,27 @@ int lmdec_quantize_planes(const double* B, int64_t ldb, int64_t Kd, int64_t kd_l
   const int kq = N / P;
   const unsigned blocks = (unsigned)cdiv(n_groups * kq, 256);
   cudaStream_t st_ = (cudaStream_t)stream;
+#define LMDEC_Q(PP) \
+  quantize_planes_kernel<PP, TB><<<blocks, 256, 0, st_>>>(B, ldb, kd_limit, K, N, mult, row1, row2, image1, image2, n_groups)
   switch (P) {
-    case 1: quantize_planes_kernel<1><<<blocks, 256, 0, st_>>>(B, ldb, kd_limit, K, N, mult, row1, row2, image1, image2, n_groups); break;
-    case 2: quantize_planes_kernel<2><<<blocks, 256, 0, st_>>>(B, ldb, kd_limit, K, N, mult, row1, row2, image1, image2, n_groups); break;
-    case 3: quantize_planes_kernel<3><<<blocks, 256, 0, st_>>>(B, ldb, kd_limit, K, N, mult, row1, row2, image1, image2, n_groups); break;
-    default: quantize_planes_kernel<4><<<blocks, 256, 0, st_>>>(B, ldb, kd_limit, K, N, mult, row1, row2, image1, image2, n_groups); break;
+    case 1: LMDEC_Q(1); break;
+    case 2: LMDEC_Q(2); break;
+    case 3: LMDEC_Q(3); break;
+    default: LMDEC_Q(4); break;
   }
+#undef LMDEC_Q
   if (kq * P < N)
     quantize_tail_kernel<<<(unsigned)cdiv(n_groups * (N - kq * P), 256), 256, 0, st_>>>(image1, image2, N, kq * P,
                                                                                         n_groups);
   return check_launch("lmdec_quantize_planes");
+}
+
+extern "C" {
+
+int lmdec_quantize_planes(const double* B, int64_t ldb, int64_t Kd, int64_t kd_limit, int K, int P, int N,
+                          const double* mult, const double* row1, const double* row2, int8_t* image1, int8_t* image2,
+                          void* stream) {
+  return quantize_planes_t<double>(B, ldb, Kd, kd_limit, K, P, N, mult, row1, row2, image1, image2, stream);
 }
 
 int lmdec_colabsmax(const double* B, int64_t ldb, int64_t kd_limit, int K, const double* row1, const double* row2,
@@ -820,7 +836,7 @@ int lmdec_finalize(const int64_t* acc0, const int64_t* acc1, int64_t M, int K, c
                    const double* rowa, const double* rowscale, const double* rowshift, const double* colshift,
                    double* out, int64_t ldo, void* stream) {
   if (acc1 && !rowa) return fail("lmdec_finalize: acc1 needs rowa");
-  finalize_kernel<<<(unsigned)cdiv(M * K, 256), 256, 0, (cudaStream_t)stream>>>(
+  finalize_kernel<double><<<(unsigned)cdiv(M * K, 256), 256, 0, (cudaStream_t)stream>>>(
       (const long long*)acc0, (const long long*)acc1, M, K, colscale, rowa, rowscale, rowshift, colshift, out, ldo);
   return check_launch("lmdec_finalize");
 }
@@ -868,13 +884,15 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
 int64_t lmdec_apply_work_doubles(int K) { return (int64_t)5 * K + (int64_t)kStatsMaxBlocks * 3 * K; }
 
 int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
-                         int has_missing, int transpose_flags, const double* B, int64_t ldb, int K, int P,
+                         int has_missing, int transpose_flags, const void* B, int64_t ldb, int K, int P,
                          const double* scale, const double* impute, const double* center_w, double* work,
-                         int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, double* out, int64_t ldo,
+                         int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, void* out, int64_t ldo,
                          void* stream) {
   if (K < 1 || K > 128 || P < 1 || P > 4) return fail("lmdec_operator_apply: bad K/P");
   const int transpose = transpose_flags & 1;
   const bool reuse_operand = (transpose_flags & 2) != 0;  // stats + plane images of B are already in work / image1/2
+  const bool b_f32 = (transpose_flags & 4) != 0;          // B is float32 (else float64)
+  const bool out_f32 = (transpose_flags & 8) != 0;        // out is float32 (else float64)
   const int N = (K * P + 15) / 16 * 16;
   if (N > 128) return fail("lmdec_operator_apply: K*P needs more than 128 tensor-core columns");
   if (has_missing && !impute) return fail("lmdec_operator_apply: has_missing needs the imputation vector");
@@ -893,16 +911,25 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
   const double lim = ldexp(1.0, 8 * P - (two ? 3 : 2));
   int rc = 0;
   if (!reuse_operand) {
-  colstats_partial_kernel<<<(unsigned)blocks, threads, 3 * threads * sizeof(double), st>>>(
-      B, ldb, kd_limit, K, transpose ? nullptr : scale, two ? impute : nullptr, transpose ? nullptr : center_w,
-      center_w != nullptr, partial);
+  if (b_f32)
+    colstats_partial_kernel<float><<<(unsigned)blocks, threads, 3 * threads * sizeof(double), st>>>(
+        (const float*)B, ldb, kd_limit, K, transpose ? nullptr : scale, two ? impute : nullptr,
+        transpose ? nullptr : center_w, center_w != nullptr, partial);
+  else
+    colstats_partial_kernel<double><<<(unsigned)blocks, threads, 3 * threads * sizeof(double), st>>>(
+        (const double*)B, ldb, kd_limit, K, transpose ? nullptr : scale, two ? impute : nullptr,
+        transpose ? nullptr : center_w, center_w != nullptr, partial);
   colstats_finish_kernel<<<1, 1024, (size_t)(1024 / K) * 3 * K * sizeof(double), st>>>(partial, (int)blocks, K, lim,
                                                                                           -1.0, stats);
   rc = check_launch("lmdec_operator_apply (colstats)", 2);
   if (rc) return rc;
   // ---- int8 planes
-  rc = lmdec_quantize_planes(B, ldb, Kd, kd_limit, K, P, N, stats, transpose ? nullptr : scale,
-                             two ? impute : nullptr, image1, two ? image2 : nullptr, stream);
+  rc = b_f32 ? quantize_planes_t<float>((const float*)B, ldb, Kd, kd_limit, K, P, N, stats,
+                                        transpose ? nullptr : scale, two ? impute : nullptr, image1,
+                                        two ? image2 : nullptr, stream)
+             : quantize_planes_t<double>((const double*)B, ldb, Kd, kd_limit, K, P, N, stats,
+                                         transpose ? nullptr : scale, two ? impute : nullptr, image1,
+                                         two ? image2 : nullptr, stream);
   if (rc) return rc;
   }
   // ---- tensor-core product, with the diagonal / rank-1 terms fused into its epilogue when it is not split
@@ -914,13 +941,19 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
   fz.rowshift = transpose ? center_w : nullptr;
   fz.out = out;
   fz.ldo = ldo;
+  fz.out_f32 = out_f32 ? 1 : 0;
   bool fused = false;
   rc = launch_geno_mma(store, M, Kd, m_limit, kd_limit, has_missing, (transpose && has_missing) ? 1 : 0, image1,
                        two ? image2 : nullptr, K, P, N, acc0, (transpose && has_missing) ? acc1 : nullptr, 0, stream,
                        &fz, &fused);
   if (rc || fused) return rc;
-  return lmdec_finalize(acc0, fz.rowa ? acc1 : nullptr, m_limit, K, fz.colscale, fz.rowa, fz.rowscale, fz.rowshift,
-                        fz.colshift, out, ldo, stream);
+  if (!out_f32)
+    return lmdec_finalize(acc0, fz.rowa ? acc1 : nullptr, m_limit, K, fz.colscale, fz.rowa, fz.rowscale, fz.rowshift,
+                          fz.colshift, (double*)out, ldo, stream);
+  finalize_kernel<float><<<(unsigned)cdiv(m_limit * K, 256), 256, 0, st>>>(
+      (const long long*)acc0, (const long long*)(fz.rowa ? acc1 : nullptr), m_limit, K, fz.colscale, fz.rowa,
+      fz.rowscale, fz.rowshift, fz.colshift, (float*)out, ldo);
+  return check_launch("lmdec_operator_apply (finalize)");
 }
 
 int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, double* r, int* flag, void* stream) {

@@ -82,5 +82,5 @@ def sym_mat_mult_start(array, k: int, seed: int = 42, log: int = 0):
     array = as_operator(array)
     omega = rnormal_start(array, k, seed=seed).t
     t = array.tdot_t(omega) if hasattr(array, "tdot_t") else array.T.dot_t(omega)
-    out = DeviceArray(array.dot_t(t))
+    out = DeviceArray(array.dot_t(t).to(F64))
     return (out, {}) if log else out

@@ -293,7 +293,7 @@ class PowerMethod(_IterAlgo):
         full_v = any(m in self.scoring_method for m in ["rmse", "v-subspace"])
         if full_v:
             # subspace_to_V (matrix_ops.py:89-99): left singular vectors of A^T x = t r; t is reused by the step
-            w = self._t(st) @ torch.as_tensor(r, device=dev)
+            w = self._t(st).to(F64) @ torch.as_tensor(r, device=dev)
             v, _, _ = tsqr_svd(w)
             V_k = DeviceArray(v.T[:k, :])
         else:
@@ -329,7 +329,7 @@ class PowerMethod(_IterAlgo):
             U, S, _ = self.history.iter["last_value"]
             st = self._cache if self._cache.get("x") is x else None
             if st is not None and "t" in st:
-                w = st["t"] @ torch.as_tensor(st["r"], device=x.device)
+                w = st["t"].to(F64) @ torch.as_tensor(st["r"], device=x.device)
                 v, _, _ = tsqr_svd(w)
                 V = DeviceArray(v.T[:self.k, :])
             else:
@@ -362,8 +362,8 @@ class _vPowerMethod(PowerMethod):
         if not self.full_svd:
             st = self._cache if self._cache.get("x") is x else None
             if st is not None and "t" in st:
-                return st["t"] @ torch.as_tensor(st["r"], device=x.device)    # A^T x = (A^T q) r
-            return _tdot(self.array, x)
+                return st["t"].to(F64) @ torch.as_tensor(st["r"], device=x.device)    # A^T x = (A^T q) r
+            return _tdot(self.array, x).to(F64)
         return PowerMethod._finalization(self, x, return_history=False)
 
 
@@ -405,7 +405,7 @@ class SuccessiveBatchedPowerMethod(PowerMethod):
             x = sub_svd_init(sub_array, k=vec_t, warm_start_row_factor=self.init_row_sampling_factor, log=0).t
         else:
             x = rnormal_start(sub_array, k=vec_t, log=0).t
-        x = _tdot(sub_array, x)
+        x = _tdot(sub_array, x).to(F64)
         for i, part in enumerate(tqdm(partitions[:-1], disable=not verbose)):
             _PM = _vPowerMethod(v_start=x, k=self.k, buffer=self.buffer, max_iter=self.max_iter, factor=self.factor,
                                 scoring_method=self.scoring_method, tol=self.tol, warn=self.warn)

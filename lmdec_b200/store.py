@@ -302,8 +302,9 @@ class GenotypeOperator:
 
     # ------------------------------------------------------------------ the two products (torch tensors in/out)
     def _apply(self, b_in: torch.Tensor, transpose: bool, out: torch.Tensor = None, m_range=None,
-               reuse_operand: bool = False) -> torch.Tensor:
-        """One lmdec_operator_apply call; `m_range` = (m0, m1) restricts the OUTPUT rows (m0 a multiple of 128)."""
+               reuse_operand: bool = False, out_dtype=F64) -> torch.Tensor:
+        """One lmdec_operator_apply call; `m_range` = (m0, m1) restricts the OUTPUT rows (m0 a multiple of 128).
+        b_in may be float64 or float32; the result is `out_dtype` (float64 or float32)."""
         st, lib = self.store, self.store.lib
         K = b_in.shape[1]
         buf = self._buffers(K)
@@ -313,7 +314,9 @@ class GenotypeOperator:
         else:
             store, M, Kd, m_lim, kd_lim = st.s_store, st.n, st.p, m, st.p
         if out is None:
-            out = torch.empty((m_lim, K), dtype=F64, device=st.device)
+            out = torch.empty((m_lim, K), dtype=out_dtype, device=st.device)
+        flags = int(transpose) | (2 if reuse_operand else 0) | (4 if b_in.dtype == torch.float32 else 0) | \
+            (8 if out.dtype == torch.float32 else 0)
         if m == 0:
             return out.zero_() if transpose else out
         m0, m1 = (0, m_lim) if m_range is None else m_range
@@ -328,14 +331,14 @@ class GenotypeOperator:
         store_ptr = C.c_void_p(store.data_ptr() + (m0 // 128) * ((Kd + 255) // 256) * 8192)
         with _timed("tdot" if transpose else "dot"):
             _capi.check(lib.lmdec_operator_apply(
-                store_ptr, M - m0, Kd, m1 - m0, kd_lim, int(miss), int(transpose) | (2 if reuse_operand else 0),
-                _capi.ptr(b_in), b_in.stride(0),
+                store_ptr, M - m0, Kd, m1 - m0, kd_lim, int(miss), flags, _capi.ptr(b_in), b_in.stride(0),
                 K, self.planes,
                 off(self.inv_std) if row_vec else _capi.ptr(self.inv_std),
                 (off(self.impute_mean) if row_vec else _capi.ptr(self.impute_mean)) if miss else None,
                 off(self._center_w()) if row_vec else _capi.ptr(self._center_w()),
                 _capi.ptr(buf["work"]), _capi.ptr(buf["im1"]), _capi.ptr(buf["im2"]),
-                _capi.ptr(buf["acc0"]), _capi.ptr(buf["acc1"]), off(out, K * 8), K, _capi.stream_ptr()),
+                _capi.ptr(buf["acc0"]), _capi.ptr(buf["acc1"]), off(out, K * out.element_size()), K,
+                _capi.stream_ptr()),
                 "lmdec_operator_apply")
         return out
 
@@ -346,59 +349,68 @@ class GenotypeOperator:
             t = t[:, None]
         if t.shape[0] != self.store.p:
             raise ValueError("shapes {} and {} not aligned".format(self.shape, tuple(t.shape)))
-        if t.stride(1) != 1 or t.dtype != F64:
-            t = t.to(F64).contiguous()
+        if t.dtype not in (F64, torch.float32):
+            t = t.to(F64)
+        if t.stride(1) != 1 or t.stride(0) != t.shape[1]:
+            t = t.contiguous()
         x = self._apply(t, False)
         return x[:, 0] if squeeze else x
 
-    def tdot_t(self, y: torch.Tensor) -> torch.Tensor:
-        """w[p, K] = A^T y  for y [n_local, K] float64 on the device (all-reduced over ranks when sharded)."""
+    @property
+    def wide_dtype(self):
+        """dtype of the p x K side of the iteration (t = A^T q) on the internal fast path; the public `.T.dot` is
+        always float64.  Row-sharded: float32 -- half the NVLink bytes of the all-reduce, and its 24-bit mantissa is finer
+        than the 22-bit fixed point t is quantised to on its next use (2 x B200: 1.28 vs 1.41 ms per iteration).  Single
+        GPU: float64 (float32 -> float64 conversions in the operand kernels cost more than the halved reads save)."""
+        env = __import__("os").environ.get("LMDEC_WIDE_DTYPE")
+        if env:
+            return {"f32": torch.float32, "f64": torch.float64}[env]
+        return torch.float32 if self.store.group is not None else torch.float64
+
+    def tdot_t(self, y: torch.Tensor, out_dtype=None) -> torch.Tensor:
+        """w[p, K] = A^T y  for y [n_local, K] on the device (all-reduced over ranks when sharded); `out_dtype`
+        defaults to `wide_dtype`."""
+        out_dtype = out_dtype or self.wide_dtype
         squeeze = y.ndim == 1
         if squeeze:
             y = y[:, None]
         if y.shape[0] != self.rows:
             raise ValueError("shapes {} and {} not aligned".format(self.shape[::-1], tuple(y.shape)))
-        if y.stride(1) != 1 or y.dtype != F64:
-            y = y.to(F64).contiguous()
+        if y.dtype not in (F64, torch.float32):
+            y = y.to(F64)
+        if y.stride(1) != 1 or y.stride(0) != y.shape[1]:
+            y = y.contiguous()
         if self.store.group is None:
-            w = self._apply(y, True)
+            w = self._apply(y, True, out_dtype=out_dtype)
         else:
-            w = self._tdot_sharded(y)
+            w = self._tdot_sharded(y, out_dtype)
         return w[:, 0] if squeeze else w
 
-    def _tdot_sharded(self, y: torch.Tensor) -> torch.Tensor:
-        """A^T y over row-sharded samples: the p x K partial products are all-reduced over NCCL.  Transport dtype
-        `store.reduce_dtype` (float32 by default: its 24-bit mantissa is finer than the 22-bit fixed point the result is
-        quantised to on its next use).  `reduce_parts` > 1 splits the product into SNP ranges and launches each range's
+    def _tdot_sharded(self, y: torch.Tensor, out_dtype) -> torch.Tensor:
+        """A^T y over row-sharded samples: the p x K partial products (float32 by default, see `wide_dtype`) are
+        all-reduced over NCCL in place.  `reduce_parts` > 1 splits the product into SNP ranges and launches each range's
         all-reduce asynchronously so that it overlaps the tensor-core work of the next range; measured on 2 x B200 the
         extra launches cost as much as the overlap wins (profiles/r01/multi_gpu_notes.txt), so the default is 1."""
         import torch.distributed as dist
         st = self.store
         K = y.shape[1]
-        w = torch.empty((st.p, K), dtype=F64, device=st.device)
+        w = torch.empty((st.p, K), dtype=out_dtype, device=st.device)
         n_tiles = (st.p + 127) // 128
         parts = max(1, min(int(getattr(st, "reduce_parts", 0) or __import__("os").environ.get("LMDEC_REDUCE_PARTS", "1")),
                            n_tiles))
-        rdt = getattr(st, "reduce_dtype", None) or _REDUCE_DTYPE
         bounds = [min(st.p, (n_tiles * i // parts) * 128) for i in range(parts)] + [st.p]
         pending = []
-        reserve = int(__import__("os").environ.get("LMDEC_SM_RESERVE", "16"))
-        st.lib.lmdec_set_sm_reserve(reserve if parts > 1 else 0)   # leave SMs for the concurrent NCCL kernels
+        if parts > 1:
+            st.lib.lmdec_set_sm_reserve(int(__import__("os").environ.get("LMDEC_SM_RESERVE", "16")))
         for i in range(parts):
             m0, m1 = bounds[i], bounds[i + 1]
             if m1 <= m0:
                 continue
             self._apply(y, True, out=w, m_range=(m0, m1), reuse_operand=bool(pending))
-            seg = w[m0:m1]
-            buf = seg if rdt == F64 else seg.to(rdt)
-            if __import__("os").environ.get("LMDEC_DEBUG_SKIP_ALLREDUCE"):
-                continue
-            pending.append((dist.all_reduce(buf, group=st.group, async_op=True), seg, buf))
+            pending.append(dist.all_reduce(w[m0:m1], group=st.group, async_op=True))
         st.lib.lmdec_set_sm_reserve(0)
-        for work, seg, buf in pending:
+        for work in pending:
             work.wait()
-            if buf is not seg:
-                seg.copy_(buf)
         return w
 
     # ------------------------------------------------------------------ materialisation (tests / small inputs)
@@ -435,7 +447,7 @@ class _Transposed:
         return self.op
 
     def dot(self, y):
-        return DeviceArray(self.op.tdot_t(as_tensor(y, self.op.store.device)))
+        return DeviceArray(self.op.tdot_t(as_tensor(y, self.op.store.device), out_dtype=F64))
 
     def dot_t(self, y):
         return self.op.tdot_t(y)
