@@ -49,14 +49,49 @@ class DenseOperator:
         out.a = self.a.T
         return out
 
+    # float32 matrices: "fp32" (default) = plain fp32 library GEMM; "tf32x3" = error-compensated split
+    # A = A_hi + A_lo, x = x_hi + x_lo on the TF32 tensor cores (A_hi x_hi + A_lo x_hi + A_hi x_lo: fp32-level accuracy).
+    # Measured on configs[4] (1M x 4k, K = 110) the three skinny cuBLAS TF32 GEMMs are slower than the fp32 one (58 vs
+    # 47 ms per iteration), so it stays opt-in until the dense path gets its own tcgen05 kernel.
+    f32_mode = __import__("os").environ.get("LMDEC_DENSE_F32", "fp32")
+
+    def _split(self):
+        if getattr(self, "_hi", None) is None:
+            hi = (self.a.view(torch.int32) & -8192).view(torch.float32)      # keep the 10 mantissa bits TF32 keeps
+            self._hi, self._lo = hi, self.a - hi
+        return self._hi, self._lo
+
+    def _mm32(self, x, transpose):
+        xf = x.to(F64)
+        if self.f32_mode != "tf32x3":
+            a = self.a.T if transpose else self.a
+            return (a @ xf.to(torch.float32)).to(F64)
+        hi, lo = self._split()
+        if transpose:
+            hi, lo = hi.T, lo.T
+        x32 = xf.to(torch.float32)
+        x_hi = (x32.view(torch.int32) & -8192).view(torch.float32)
+        x_lo = x32 - x_hi
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            out = (hi @ x_hi).to(F64) + (lo @ x_hi).to(F64) + (hi @ x_lo).to(F64)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        return out
+
     def dot_t(self, x):
         if x.shape[0] != self.a.shape[1]:
             raise ValueError("shapes {} and {} not aligned".format(self.shape, tuple(x.shape)))
+        if self.a.dtype == torch.float32:
+            return self._mm32(x, False)
         return (self.a @ x.to(self.a.dtype)).to(F64)
 
     def tdot_t(self, y):
         if y.shape[0] != self.a.shape[0]:
             raise ValueError("shapes {} and {} not aligned".format(self.shape[::-1], tuple(y.shape)))
+        if self.a.dtype == torch.float32:
+            return self._mm32(y, True)
         return (self.a.T @ y.to(self.a.dtype)).to(F64)
 
     def dot(self, x):

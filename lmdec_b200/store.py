@@ -139,6 +139,31 @@ class GenotypeStore:
         self.finish()
         return self
 
+    # ------------------------------------------------------------------ persistence (reference array/io.py:129-273)
+    def save(self, path: str):
+        """Write the packed store (both orientations + shape) so that packing / the NaN scan is not repeated.
+        Stands where save_array / load_array_from_disk store the operator's members as zarr trees."""
+        import os
+        os.makedirs(path, exist_ok=True)
+        torch.save({"n": self.n, "p": self.p, "n_global": self.n_global, "row_offset": self.row_offset,
+                    "format": "lmdec_b200 tile store v1 (2-bit dosage codes, 3 = missing; 128 x 256 tiles)"},
+                   os.path.join(path, "meta.pt"))
+        np.save(os.path.join(path, "sample_major.npy"), self.s_store.cpu().numpy())
+        np.save(os.path.join(path, "snp_major.npy"), self.v_store.cpu().numpy())
+
+    @classmethod
+    def load(cls, path: str, device=None, group=None):
+        import os
+        meta = torch.load(os.path.join(path, "meta.pt"))
+        self = cls(meta["n"], meta["p"], device=device, group=group, n_global=meta["n_global"],
+                   row_offset=meta["row_offset"])
+        for name, dst in (("sample_major.npy", self.s_store), ("snp_major.npy", self.v_store)):
+            src = torch.from_numpy(np.load(os.path.join(path, name), mmap_mode="r")[:])
+            if src.numel() != dst.numel():
+                raise ValueError("stored tile store does not match its recorded shape")
+            dst.copy_(src)
+        return self
+
     def finish(self):
         bad = int(self._bad.item())
         if bad:

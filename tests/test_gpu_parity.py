@@ -301,3 +301,45 @@ def test_full_size_properties_config1(cuda):
     ones = torch.ones((n, 1), dtype=torch.float64, device=cuda)
     col_sums = op.tdot_t(ones)[:, 0]                              # 1^T A = 0 for a centred, mean-imputed operator
     assert col_sums.abs().max().item() <= 1e-4 * np.sqrt(n)
+
+
+def test_store_save_load_and_bed_roundtrip(cuda, tmp_path):
+    """persistence of the packed operator (reference array/io.py save_array / load_array_from_disk) and the .bed loader."""
+    import torch
+    from lmdec_b200.store import GenotypeOperator, GenotypeStore
+    g = synth_genotypes(300, 517, 0.06, seed=12)
+    st = GenotypeStore.from_dense(g)
+    st.save(str(tmp_path / "store"))
+    st2 = GenotypeStore.load(str(tmp_path / "store"))
+    assert torch.equal(st.s_store, st2.s_store) and torch.equal(st.v_store, st2.v_store)
+    assert torch.equal(st.code_counts(), st2.code_counts())
+    # .bed payload: variant-major PLINK codes (00 -> 0, 01 -> missing, 10 -> 1, 11 -> 2)
+    dosage_to_plink = {0: 0, 1: 2, 2: 3}
+    codes = np.vectorize(lambda v: 1 if np.isnan(v) else dosage_to_plink[int(v)])(g.T).astype(np.uint8)   # [p, n]
+    bpv = (300 + 3) // 4
+    padded = np.zeros((517, bpv * 4), dtype=np.uint8)
+    padded[:, :300] = codes
+    bed = (padded[:, 0::4] | (padded[:, 1::4] << 2) | (padded[:, 2::4] << 4) | (padded[:, 3::4] << 6)).astype(np.uint8)
+    st3 = GenotypeStore.from_bed_bytes(bed.tobytes(), n_samples=300, n_variants=517)
+    assert torch.equal(st3.s_store, st.s_store) and torch.equal(st3.v_store, st.v_store)
+
+
+def test_dense_float32_tf32x3_matches_float64(cuda):
+    """float32 dense inputs (configs[4] path): the error-compensated TF32 split keeps fp32-level accuracy."""
+    from lmdec_b200.array import ChainedArray
+    from lmdec_b200.array.operators import DenseOperator
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((3000, 500)).astype(np.float32)
+    x, y = rng.standard_normal((500, 12)), rng.standard_normal((3000, 12))
+    op = DenseOperator(a, keep_dtype=True)
+    assert op.a.dtype.is_floating_point and op.a.element_size() == 4
+    op.f32_mode = "tf32x3"
+    import torch
+    ref_ax, ref_aty = a.astype(np.float64) @ x, a.astype(np.float64).T @ y
+    ax, aty = op.dot_t(torch.as_tensor(x, device=cuda)).cpu().numpy(), op.tdot_t(torch.as_tensor(y, device=cuda)).cpu().numpy()
+    assert np.max(np.abs(ax - ref_ax)) <= 2e-5 * np.max(np.abs(ref_ax))
+    assert np.max(np.abs(aty - ref_aty)) <= 2e-5 * np.max(np.abs(ref_aty))
+    from lmdec_b200 import PowerMethod
+    u, s, v = np.linalg.svd(a.astype(np.float64), full_matrices=False)
+    U, S, V = PowerMethod(k=3, buffer=10, tol=1e-10, factor=None, lmbd=0, max_iter=300).svd(ChainedArray([a]), verbose=False)
+    np.testing.assert_allclose(_np(S), s[:3], rtol=1e-5)
