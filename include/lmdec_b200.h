@@ -151,6 +151,14 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
  * place of dask tsqr's stacked-R QR (lmdec/decomp/iter_methods.py:382).  */
 int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, double* r, int* flag, void* stream);
 
+/* Single-GPU fast path of one CholeskyQR pass: Gram matrix of X (deterministic partials, summed inside the
+ * factorisation kernel) and its Cholesky whitening, two launches.  G receives X^T X.  work: lmdec_gram_work_doubles. */
+int lmdec_gram_chol(const double* X, int64_t ldx, int64_t m, int K, double rank_tol, double* G, double* r_inv,
+                    double* r, int* flag, double* work, void* stream);
+/* packed[0..K*K) = r2 r1, then flag1, flag2, max|g2 - I|: what the host reads back from one CholeskyQR2. */
+int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const int* flag1, const int* flag2, int K,
+                  double* packed, void* stream);
+
 /* Leave `n_sms` SMs out of the persistent product kernel's grid so that a collective (NCCL) launched on another stream
  * can run concurrently with it; 0 (default) = use every SM.  Process-wide setting. */
 void lmdec_set_sm_reserve(int n_sms);

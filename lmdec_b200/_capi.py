@@ -34,6 +34,8 @@ SIGNATURES = {
     "lmdec_operator_apply": (_i32, [_p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p,
                                     _p, _p, _p, _i64, _p]),
     "lmdec_chol_whiten": (_i32, [_p, _i32, C.c_double, _p, _p, _p, _p]),
+    "lmdec_gram_chol": (_i32, [_p, _i64, _i64, _i32, C.c_double, _p, _p, _p, _p, _p, _p]),
+    "lmdec_qr_pack": (_i32, [_p, _p, _p, _p, _p, _i32, _p, _p]),
     "lmdec_kernel_timing": (None, [_i32]),
     "lmdec_set_sm_reserve": (None, [_i32]),
     "lmdec_set_pair_mode": (None, [_i32]),

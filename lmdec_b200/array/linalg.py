@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ..device import F64, chol_whiten, gram
+from ..device import F64, chol_whiten, gram, gram_chol, qr_pack
 
 
 def _allreduce(t: torch.Tensor, group):
@@ -130,15 +130,18 @@ def orthonormalize_begin(x: torch.Tensor, group=None) -> _PendingQR:
     """Enqueue CholeskyQR2 entirely on the device (both K x K factorizations included) and return without syncing, so
     the caller can queue the next products behind it before asking for r."""
     K = x.shape[1]
-    G1 = _allreduce(gram(x), group)
-    ri1, r1, f1 = chol_whiten(G1)
-    q1 = x @ ri1
-    G2 = _allreduce(gram(q1), group)
-    ri2, r2, f2 = chol_whiten(G2)
+    if group is None:
+        _, ri1, r1, f1 = gram_chol(x)                  # 2 launches per pass, nothing else
+        q1 = x @ ri1
+        G2, ri2, r2, f2 = gram_chol(q1)
+    else:
+        G1 = _allreduce(gram(x), group)
+        ri1, r1, f1 = chol_whiten(G1)
+        q1 = x @ ri1
+        G2 = _allreduce(gram(q1), group)
+        ri2, r2, f2 = chol_whiten(G2)
     q = q1 @ ri2
-    r = r2 @ r1
-    dev2 = (G2 - torch.eye(K, dtype=F64, device=x.device)).abs().max().reshape(1)
-    packed = torch.cat([r.reshape(-1), f1.to(F64), f2.to(F64), dev2])
+    packed = qr_pack(r1, r2, G2, f1, f2)
     return _PendingQR(q, packed, K)
 
 

@@ -481,9 +481,12 @@ __global__ void gram_final_kernel(const double* __restrict__ work, int n_blocks,
 //   r_inv [K,K] and r [K,K] row-major (upper triangular), flag = 1 when G is non-finite, has a non-positive diagonal or
 //   a pivot below rank_tol (the caller then takes the rank-revealing host path).  Replaces the K x K step of dask tsqr
 //   (lmdec/decomp/iter_methods.py:382) without a device->host round trip.
+// `n_partials` > 0: G is not a matrix but the per-block partial Gram matrices of gram_partial_kernel (stride
+// K*K + K); they are summed here in block order (deterministic) and the sum is also written to g_out.
 __global__ void __launch_bounds__(128) chol_whiten_kernel(const double* __restrict__ G, int K, double rank_tol,
                                                           double* __restrict__ r_inv, double* __restrict__ r,
-                                                          int* __restrict__ flag) {
+                                                          int* __restrict__ flag, int n_partials,
+                                                          double* __restrict__ g_out) {
   extern __shared__ double sm[];
   double* L = sm;            // [K][K] lower factor of the scaled Gram matrix
   double* Li = sm + K * K;   // [K][K] inverse of L (lower)
@@ -491,6 +494,16 @@ __global__ void __launch_bounds__(128) chol_whiten_kernel(const double* __restri
   __shared__ int bad;
   const int t = threadIdx.x;
   if (t == 0) bad = 0;
+  if (n_partials > 0) {
+    const int stride = K * K + K;
+    for (int i = t; i < K * K; i += blockDim.x) {
+      double a = 0.0;
+      for (int b = 0; b < n_partials; ++b) a += G[(size_t)b * stride + i];
+      g_out[i] = a;
+    }
+    __syncthreads();
+    G = g_out;
+  }
   __syncthreads();
   if (t < K) {
     const double g = G[t * K + t];
@@ -964,8 +977,57 @@ int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, do
     cudaFuncSetAttribute(chol_whiten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     attr_set = true;
   }
-  chol_whiten_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(G, K, rank_tol, r_inv, r, flag);
+  chol_whiten_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(G, K, rank_tol, r_inv, r, flag, 0, nullptr);
   return check_launch("lmdec_chol_whiten");
+}
+
+// packed[0 .. K*K) = r2 r1,  packed[K*K] = flag1, [K*K+1] = flag2, [K*K+2] = max |G2 - I|: everything the host needs
+// from one CholeskyQR2 in a single contiguous buffer (one device->host copy per iterate).
+__global__ void qr_pack_kernel(const double* __restrict__ r1, const double* __restrict__ r2,
+                               const double* __restrict__ g2, const int* __restrict__ f1, const int* __restrict__ f2,
+                               int K, double* __restrict__ packed) {
+  __shared__ double red[128];
+  const int t = threadIdx.x;
+  double dev = 0.0;
+  for (int i = t; i < K * K; i += blockDim.x) {
+    const int a = i / K, b = i - a * K;
+    double acc = 0.0;
+    for (int c = a; c <= b; ++c) acc += r2[a * K + c] * r1[c * K + b];  // both factors are upper triangular
+    packed[i] = acc;
+    const double g = g2[i] - (a == b ? 1.0 : 0.0);
+    dev = fmax(dev, g == g ? fabs(g) : INFINITY);
+  }
+  red[t] = dev;
+  __syncthreads();
+  if (t == 0) {
+    for (int i = 1; i < blockDim.x; ++i) dev = fmax(dev, red[i]);
+    packed[K * K] = (double)*f1;
+    packed[K * K + 1] = (double)*f2;
+    packed[K * K + 2] = dev;
+  }
+}
+
+int lmdec_gram_chol(const double* X, int64_t ldx, int64_t m, int K, double rank_tol, double* G, double* r_inv,
+                    double* r, int* flag, double* work, void* stream) {
+  if (K < 1 || K > 128) return fail("lmdec_gram_chol: K out of range (1..128)");
+  const int nb = gram_blocks(m);
+  cudaStream_t st = (cudaStream_t)stream;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(chol_whiten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    attr_set = true;
+  }
+  gram_partial_kernel<<<nb, 256, (size_t)kGramRows * K * sizeof(double), st>>>(X, ldx, nullptr, 0, m, K, work);
+  chol_whiten_kernel<<<1, 128, (size_t)(2 * K * K + K) * sizeof(double), st>>>(work, K, rank_tol, r_inv, r, flag, nb, G);
+  return check_launch("lmdec_gram_chol", 2);
+}
+
+int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const int* flag1, const int* flag2, int K,
+                  double* packed, void* stream) {
+  if (K < 1 || K > 128) return fail("lmdec_qr_pack: K out of range (1..128)");
+  qr_pack_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(r1, r2, g2, flag1, flag2, K, packed);
+  return check_launch("lmdec_qr_pack");
 }
 
 // ---- CUDA-event timing of the dominant kernel (bench.py's roofline): events are recorded on the launching stream

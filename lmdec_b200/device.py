@@ -204,3 +204,29 @@ def chol_whiten(G: torch.Tensor, rank_tol: float = 1e-12):
     _capi.check(lib.lmdec_chol_whiten(_capi.ptr(G), K, float(rank_tol), _capi.ptr(r_inv), _capi.ptr(r),
                                       _capi.ptr(flag), _capi.stream_ptr()), "lmdec_chol_whiten")
     return r_inv, r, flag
+
+
+def gram_chol(x: torch.Tensor, rank_tol: float = 1e-12):
+    """Gram matrix + Cholesky whitening of a LOCAL iterate in two launches: (G, r_inv, r, flag) on the device."""
+    lib = _capi.load()
+    x = _rows(x)
+    m, K = x.shape
+    dev = x.device
+    G = torch.empty((K, K), dtype=F64, device=dev)
+    r_inv = torch.empty((K, K), dtype=F64, device=dev)
+    r = torch.empty((K, K), dtype=F64, device=dev)
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    work = _work(dev, lib.lmdec_gram_work_doubles(m, K))
+    _capi.check(lib.lmdec_gram_chol(_capi.ptr(x), x.stride(0), m, K, float(rank_tol), _capi.ptr(G), _capi.ptr(r_inv),
+                                    _capi.ptr(r), _capi.ptr(flag), _capi.ptr(work), _capi.stream_ptr()),
+                "lmdec_gram_chol")
+    return G, r_inv, r, flag
+
+
+def qr_pack(r1, r2, g2, f1, f2) -> torch.Tensor:
+    lib = _capi.load()
+    K = r1.shape[0]
+    packed = torch.empty(K * K + 3, dtype=F64, device=r1.device)
+    _capi.check(lib.lmdec_qr_pack(_capi.ptr(r1), _capi.ptr(r2), _capi.ptr(g2), _capi.ptr(f1), _capi.ptr(f2), K,
+                                  _capi.ptr(packed), _capi.stream_ptr()), "lmdec_qr_pack")
+    return packed
