@@ -57,7 +57,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
+    path = os.environ.get("LMDEC_LIB") or _build.LIB      # LMDEC_LIB: A/B a differently built library
     if not os.path.exists(path):
         path = _build.build()
     lib = C.CDLL(path)

@@ -7,18 +7,20 @@
 // Replaces the chunked int8->f64 matmuls under PowerMethod._solution_step (reference
 // lmdec/decomp/iter_methods.py:381-386 -> lmdec/array/stacked.py:172-217, chained.py:169-177).
 //
-// CTA = 16 warps, one CTA per SM, persistent over work items (m-tile, k-split).  Every role streams across work-item
+// CTA = 20 warps, one CTA per SM, persistent over work items (m-tile, k-split).  Every role streams across work-item
 // boundaries, so HBM latency is paid once per launch, not once per tile:
 //   warps 0-7   producers: read their row of the packed tile from the smem ring (conflict-free 16-byte pieces), decode
 //               2-bit -> uint8 in registers, tcgen05.st straight into the TMEM A ring
 //   warp  8     tile loader: one thread, cp.async.bulk (TMA engine) of whole 8 KB store tiles into an 8-deep smem ring
-//   warp  15    B loader: one thread, cp.async.bulk of the pre-laid-out plane image into its own smem ring
+//   warp  19    B loader: one thread, cp.async.bulk of the pre-laid-out plane image into its own smem ring
 //   warps 9,10  MMA issuers: one thread each.  A narrow-N tcgen05.mma is limited by the issuing thread (~45-54 cycles
 //               per instruction, profiles/r01/umma_probe4_issuers.log); two issuers reach the N/2-cycle math rate.
 //               Without missing data they take alternate K-blocks; with missing data issuer 0 runs the value plane and
 //               issuer 1 the indicator plane.  Each owns one accumulator of the current accumulator set.
-//   warps 11-14 epilogue: TMEM -> registers -> exact int64 plane combine -> global (store or atomicAdd).
+//   warps 11-18 epilogue (two per TMEM lane quarter, splitting the column groups): TMEM -> registers -> exact plane
+//               combine -> global (finalized float, int64 store, or int64 atomicAdd for split-K).
 //               With N <= 64 there are two accumulator sets, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp  19    B loader (see above)
 #pragma once
 #include "umma.cuh"
 
@@ -31,10 +33,13 @@ constexpr int kProducerWarps = LMDEC_PRODUCER_WARPS;          // 8 or 16 (4 lane
 constexpr int kKbPerProducer = 32 / kProducerWarps;           // K-blocks of a chunk decoded by one producer thread
 constexpr int kTileLoaderWarp = kProducerWarps;
 constexpr int kIssuerWarp0 = kProducerWarps + 1;
-constexpr int kEpilogueWarp0 = kProducerWarps + 3;            // 4 consecutive warps cover the 4 TMEM lane quarters
-constexpr int kEpilogueWarps = 4;
-constexpr int kBLoaderWarp = kProducerWarps + 7;
-constexpr int kThreads = (kProducerWarps + 8) * 32;
+#ifndef LMDEC_EPILOGUE_WARPS
+#define LMDEC_EPILOGUE_WARPS 8
+#endif
+constexpr int kEpilogueWarp0 = kProducerWarps + 3;            // consecutive warps cover the 4 TMEM lane quarters
+constexpr int kEpilogueWarps = LMDEC_EPILOGUE_WARPS;          // 4, or 8 (two warps per quarter split the column groups)
+constexpr int kBLoaderWarp = kEpilogueWarp0 + kEpilogueWarps;
+constexpr int kThreads = (kBLoaderWarp + 1) * 32;
 constexpr int kKbPerChunk = 8;             // 8 K-blocks of 32 = one 256-wide contraction chunk = one store tile
 constexpr uint32_t kARingCol0 = 256;       // TMEM A ring: columns [256, 512); accumulators: [0, 256)
 constexpr int kMaxBStages = 4;
@@ -156,6 +161,8 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
   const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
   const int K = p.K;
   const int n_groups = (K + 7) / 8;
+  constexpr int kSplit = kEpilogueWarps / 4;                  // warps per lane quarter
+  const int g_first = (warp - kEpilogueWarp0) / 4;            // this warp takes column groups g_first, g_first + kSplit, ..
   const int n_work = p.m_units * p.splits;
   const int shift1 = p.has_missing ? kMissShift : kValueShift;
   const int tiles_per_item = p.pair ? 2 : 1;
@@ -186,7 +193,13 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
         fdst32 = (float*)p.fz.out + m * p.fz.ldo;
       }
       const double row_a3 = (row_a - 3.0) * row_scale;  // MODE 1: out = rs*(acc0 - 3 acc1) + rs*ra*acc1
-      for (int g = 0; g < n_groups; ++g) {
+      if (g_first >= n_groups && t == tiles_per_item - 1) {
+        // no column group for this warp (K <= 8 with two warps per quarter): it still takes part in the hand-back
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(acc_empty + 8 * set);
+      }
+      for (int g = g_first; g < n_groups; g += kSplit) {
         uint32_t r0[8 * P], r1[8 * P];
         const uint32_t col = (uint32_t)g * 8 * P;
 #pragma unroll
@@ -199,8 +212,8 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
           for (int i = 0; i < P; ++i) tmem_ld8p(acc1 + col + i * 8, r1 + 8 * i);
         }
         tmem_wait_ld();
-        if (g == n_groups - 1 && t == tiles_per_item - 1) {
-          // all TMEM reads of this work item are done: hand the accumulators back to the issuers
+        if (g + kSplit >= n_groups && t == tiles_per_item - 1) {
+          // this warp's TMEM reads of the work item are done: hand the accumulators back to the issuers
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive_a(acc_empty + 8 * set);
