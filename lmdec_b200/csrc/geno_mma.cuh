@@ -41,13 +41,14 @@ constexpr int kEpilogueWarps = LMDEC_EPILOGUE_WARPS;          // 4, or 8 (two wa
 constexpr int kBLoaderWarp = kEpilogueWarp0 + kEpilogueWarps;
 constexpr int kThreads = (kBLoaderWarp + 1) * 32;
 constexpr int kKbPerChunk = 8;             // 8 K-blocks of 32 = one 256-wide contraction chunk = one store tile
-constexpr uint32_t kARingCol0 = 256;       // TMEM A ring: columns [256, 512); accumulators: [0, 256)
+// TMEM: accumulators from column 0, the decoded-A ring behind them up to column 512 (p.a_ring_col0, p.a_stages)
 constexpr int kMaxBStages = 4;
 constexpr int kMaxTileStages = 8;
 constexpr uint32_t kTileBytes = 8192;
 // mbarrier slots (8 bytes each) in one shared array, addressed by 32-bit shared-window addresses
-constexpr int kBarFullT = 0, kBarEmptyT = 8, kBarFullA = 16, kBarEmptyA = 20, kBarFullB = 24, kBarEmptyB = 28,
-              kBarAccFull = 32, kBarAccEmpty = 34, kNumBars = 36;
+constexpr int kMaxAStages = 8;
+constexpr int kBarFullT = 0, kBarEmptyT = 8, kBarFullA = 16, kBarEmptyA = 24, kBarFullB = 32, kBarEmptyB = 36,
+              kBarAccFull = 40, kBarAccEmpty = 42, kNumBars = 44;
 
 // out[m,k] = (acc0 + rowa[m]*acc1) * colscale[k] * rowscale[m] + rowshift[m] * colshift[k]   (NULL = absent / 1)
 struct FusedFinalize {
@@ -79,6 +80,9 @@ struct GenoMmaParams {
   int b_stages;
   int tile_stages;
   int use_atomics;
+  int acc_sets;            // accumulator sets alternated between consecutive work items (1 or 2; 1 in pair mode)
+  int a_ring_col0;         // first TMEM column of the decoded-A ring (= columns taken by the accumulators)
+  int a_stages;            // stages of the decoded-A ring: (512 - a_ring_col0) / (128 with missing data, else 64)
   int pair;                // 0: one m-tile per work item; 1/2/3: TWO m-tiles share every B stage (kPairM/E/T)
   int m_units;             // work items per split: m_tiles, or ceil(m_tiles / 2) in pair mode
   int fuse;                // write the finalized float64 result from the epilogue (never with atomics)
@@ -303,9 +307,10 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   uint8_t* smem_t = smem;                                              // tile ring
   uint8_t* smem_b = smem + (size_t)p.tile_stages * kTileBytes;         // B ring
   const uint32_t smem_t_a = smem_u32(smem_t), smem_b_a = smem_u32(smem_b);
-  const int a_stages = p.has_missing ? 2 : 4;
+  const int a_stages = p.a_stages;
+  const uint32_t kARingCol0 = (uint32_t)p.a_ring_col0;
   const uint32_t a_stage_cols = p.has_missing ? 128 : 64;
-  const int acc_sets = N <= 64 ? 2 : 1;
+  const int acc_sets = p.acc_sets;
   const uint32_t acc_w = N <= 64 ? 64 : 128;
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       mbar_init(&bars[kBarFullT + i], 1);
       mbar_init(&bars[kBarEmptyT + i], kProducerWarps);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kMaxAStages; ++i) {
       mbar_init(&bars[kBarFullA + i], kProducerWarps);
       mbar_init(&bars[kBarEmptyA + i], p.pair == kPairT ? 1 : 2);
     }

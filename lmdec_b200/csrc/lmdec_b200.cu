@@ -768,6 +768,23 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
     else if (!has_missing) p.pair = kPairT;
   }
   p.m_units = p.pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  // TMEM budget (512 columns): accumulators first, the rest is the decoded-A ring.  Short contractions alternate two
+  // accumulator sets so the epilogue overlaps the next tile; long ones (epilogue negligible) give the columns to a
+  // deeper A ring instead.
+  {
+    const int acc_w = N <= 64 ? 64 : 128;
+    int acc_cols;
+    if (p.pair) {
+      p.acc_sets = 1;
+      acc_cols = (p.pair == kPairT ? 2 : 4) * acc_w;
+    } else {
+      p.acc_sets = (N <= 64 && p.n_chunks < 64) ? 2 : 1;
+      acc_cols = p.acc_sets * 2 * acc_w;
+    }
+    p.a_ring_col0 = acc_cols;
+    p.a_stages = (512 - acc_cols) / (has_missing ? 128 : 64);
+    if (p.a_stages > kMaxAStages) p.a_stages = kMaxAStages;
+  }
   // split-K: minimise the makespan  ceil(work / SMs) * (chunks per split + per-item overhead)  over the split count;
   // the int32 accumulators cap a split at 256 chunks (value bytes are 64*code: 64 * 3 * 127 * 65536 < 2^31)
   int want = splits;
