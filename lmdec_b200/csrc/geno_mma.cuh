@@ -7,20 +7,21 @@
 // Replaces the chunked int8->f64 matmuls under PowerMethod._solution_step (reference
 // lmdec/decomp/iter_methods.py:381-386 -> lmdec/array/stacked.py:172-217, chained.py:169-177).
 //
-// CTA = 20 warps, one CTA per SM, persistent over work items (m-tile, k-split).  Every role streams across work-item
-// boundaries, so HBM latency is paid once per launch, not once per tile:
+// CTA = 22 warps, one CTA per SM, persistent over work items (m-tile or m-tile pair, k-split).  Every role streams
+// across work-item boundaries, so HBM latency is paid once per launch, not once per tile:
 //   warps 0-7   producers: read their row of the packed tile from the smem ring (conflict-free 16-byte pieces), decode
 //               2-bit -> uint8 in registers, tcgen05.st straight into the TMEM A ring
 //   warp  8     tile loader: one thread, cp.async.bulk (TMA engine) of whole 8 KB store tiles into an 8-deep smem ring
-//   warp  19    B loader: one thread, cp.async.bulk of the pre-laid-out plane image into its own smem ring
-//   warps 9,10  MMA issuers: one thread each.  A narrow-N tcgen05.mma is limited by the issuing thread (~45-54 cycles
-//               per instruction, profiles/r01/umma_probe4_issuers.log); two issuers reach the N/2-cycle math rate.
-//               Without missing data they take alternate K-blocks; with missing data issuer 0 runs the value plane and
-//               issuer 1 the indicator plane.  Each owns one accumulator of the current accumulator set.
-//   warps 11-18 epilogue (two per TMEM lane quarter, splitting the column groups): TMEM -> registers -> exact plane
-//               combine -> global (finalized float, int64 store, or int64 atomicAdd for split-K).
-//               With N <= 64 there are two accumulator sets, so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   warp  19    B loader (see above)
+//   warps 9-12  MMA issuers: one elected lane each.  A narrow-N tcgen05.mma is limited by the issuing thread (~45-54
+//               cycles per instruction, profiles/r01/umma_probe4_issuers.log), so the MMAs of a chunk are spread over
+//               several issuers, each owning one accumulator: 2 issuers = (value plane, indicator plane) with missing
+//               data or (even, odd K-blocks) without; 4 issuers in pair mode M = (tile, plane).
+//   warps 13-20 epilogue (two per TMEM lane quarter, splitting the column groups): TMEM -> registers -> exact plane
+//               combine -> global (finalized float, int64 store, or int64 atomicAdd for split-K).  Short contractions
+//               alternate two accumulator sets, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp  21    B loader: one thread, cp.async.bulk of the pre-laid-out plane image into its own smem ring
+// Pair mode (long contractions): two m-tiles are processed against every staged chunk of the operand image, halving the
+// image's L2 -> SM traffic (it is re-read by every m-tile and dominates the product's on-chip traffic).
 #pragma once
 #include "umma.cuh"
 
@@ -33,10 +34,14 @@ constexpr int kProducerWarps = LMDEC_PRODUCER_WARPS;          // 8 or 16 (4 lane
 constexpr int kKbPerProducer = 32 / kProducerWarps;           // K-blocks of a chunk decoded by one producer thread
 constexpr int kTileLoaderWarp = kProducerWarps;
 constexpr int kIssuerWarp0 = kProducerWarps + 1;
+#ifndef LMDEC_ISSUER_WARPS
+#define LMDEC_ISSUER_WARPS 4
+#endif
+constexpr int kIssuerWarps = LMDEC_ISSUER_WARPS;              // 2, or 4 (pair mode M: one issuer per (tile, plane))
 #ifndef LMDEC_EPILOGUE_WARPS
 #define LMDEC_EPILOGUE_WARPS 8
 #endif
-constexpr int kEpilogueWarp0 = kProducerWarps + 3;            // consecutive warps cover the 4 TMEM lane quarters
+constexpr int kEpilogueWarp0 = kProducerWarps + 1 + kIssuerWarps;  // consecutive warps cover the 4 TMEM lane quarters
 constexpr int kEpilogueWarps = LMDEC_EPILOGUE_WARPS;          // 4, or 8 (two warps per quarter split the column groups)
 constexpr int kBLoaderWarp = kEpilogueWarp0 + kEpilogueWarps;
 constexpr int kThreads = (kBLoaderWarp + 1) * 32;
@@ -308,6 +313,10 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   uint8_t* smem_b = smem + (size_t)p.tile_stages * kTileBytes;         // B ring
   const uint32_t smem_t_a = smem_u32(smem_t), smem_b_a = smem_u32(smem_b);
   const int a_stages = p.a_stages;
+  // pair mode M with 4 issuer warps: one issuer per (tile, plane) accumulator, so each thread issues 8 instead of 16
+  // MMAs per staged operand chunk (a single thread sustains one narrow MMA per ~54 cycles)
+  const bool quad = kIssuerWarps == 4 && p.pair == kPairM;
+  const int n_issuers = quad ? 4 : 2;
   const uint32_t kARingCol0 = (uint32_t)p.a_ring_col0;
   const uint32_t a_stage_cols = p.has_missing ? 128 : 64;
   const int acc_sets = p.acc_sets;
@@ -330,10 +339,10 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     }
     for (int i = 0; i < kMaxBStages; ++i) {
       mbar_init(&bars[kBarFullB + i], 1);
-      mbar_init(&bars[kBarEmptyB + i], 2);
+      mbar_init(&bars[kBarEmptyB + i], n_issuers);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars[kBarAccFull + i], 2);
+      mbar_init(&bars[kBarAccFull + i], n_issuers);
       mbar_init(&bars[kBarAccEmpty + i], kEpilogueWarps);
     }
     mbar_fence_init();
@@ -438,13 +447,15 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
         }
       }
     }
-  } else if (warp == kIssuerWarp0 || warp == kIssuerWarp0 + 1) {
+  } else if (warp >= kIssuerWarp0 && warp < kIssuerWarp0 + kIssuerWarps) {
     // ------------------------------------------------------------------ MMA issuers
     // The whole warp runs the loop (uniform control flow keeps the operand arithmetic on the uniform datapath); one
     // elected lane issues.  With a plain `if (lane == 0)` ptxas wraps every UTCIMMA operand in an
     // ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~100 cycles per MMA, profiles/r01).
-    {
-      const int me = warp - kIssuerWarp0;
+    if (warp - kIssuerWarp0 < n_issuers) {
+      const int issuer = warp - kIssuerWarp0;
+      const int me = issuer & 1;            // plane (missing data) or K-block parity
+      const int my_tile = issuer >> 1;      // quad mode: the tile of the pair this issuer owns
       const uint32_t idesc = make_idesc_i8(128, (uint32_t)N, 0, 1);
       const uint32_t lbo = (uint32_t)N * 16;
       const uint32_t plane = p.has_missing ? (uint32_t)me : 0u;
@@ -471,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             if (t < tiles_per_item) {
-              const bool mine = p.pair != kPairT || t == me;
+              const bool mine = quad ? (t == my_tile) : (p.pair != kPairT || t == me);
               if (mine) {
                 mbar_wait_a(full_a + 8 * a_stage, a_phase);
                 tc_fence_after_sync();
