@@ -32,6 +32,7 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_mma_events;
 static bool g_mma_timing = false;
 static int g_sm_reserve = 0;
+static int g_pair_min_chunks = 64;
 static int g_pair_mode = 1;   // lmdec_set_pair_mode: 0 disables the two-tiles-per-B-stage schedule (A/B tests)  // SMs left free for concurrently running collectives (row-sharded runs)
 
 namespace lmdec {
@@ -762,7 +763,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
   // pair mode: two m-tiles share every staged chunk of the operand image (halves the dominant L2 -> SM traffic).  Only
   // for long contractions (the accumulators are not double-buffered across work items) and when TMEM has room.
   p.pair = kPairNone;
-  if (p.m_tiles >= 2 && p.n_chunks >= 64 && g_pair_mode) {
+  if (p.m_tiles >= 2 && p.n_chunks >= g_pair_min_chunks && g_pair_mode) {
     if (has_missing && N <= 64) p.pair = kPairM;
     else if (!has_missing && N <= 64) p.pair = kPairE;
     else if (!has_missing) p.pair = kPairT;
@@ -778,7 +779,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
       p.acc_sets = 1;
       acc_cols = (p.pair == kPairT ? 2 : 4) * acc_w;
     } else {
-      p.acc_sets = (N <= 64 && p.n_chunks < 64) ? 2 : 1;
+      p.acc_sets = (N <= 64 && p.n_chunks < g_pair_min_chunks) ? 2 : 1;
       acc_cols = p.acc_sets * 2 * acc_w;
     }
     p.a_ring_col0 = acc_cols;
@@ -1048,7 +1049,10 @@ int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const in
 }
 
 // ---- CUDA-event timing of the dominant kernel (bench.py's roofline): events are recorded on the launching stream
-void lmdec_set_pair_mode(int on) { g_pair_mode = on != 0; }
+void lmdec_set_pair_mode(int on) {
+  g_pair_mode = on != 0;
+  if (on > 1) g_pair_min_chunks = on;  // values > 1 also set the shortest contraction (in 256-wide chunks) that pairs
+}
 
 void lmdec_set_sm_reserve(int n_sms) { g_sm_reserve = n_sms < 0 ? 0 : n_sms; }
 
