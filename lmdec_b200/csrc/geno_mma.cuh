@@ -67,6 +67,15 @@ struct FusedFinalize {
   int out_f32;
 };
 
+#ifdef LMDEC_TRACE
+// debug timeline: CTA 0 records clock64() stamps of its first kTraceChunks chunks (tools/trace_mma.py prints them)
+constexpr int kTraceChunks = 64;
+__device__ long long g_trace[8][kTraceChunks];
+#define LMDEC_STAMP(row, idx) do { if (blockIdx.x == 0 && (idx) < kTraceChunks) g_trace[row][idx] = clock64(); } while (0)
+#else
+#define LMDEC_STAMP(row, idx) do { } while (0)
+#endif
+
 struct GenoMmaParams {
   const uint8_t* store;
   long long store_kc;      // chunks per row panel in the store (tile stride)
@@ -363,6 +372,9 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
     const uint32_t my_off = (uint32_t)((kKbPerProducer / 2) * half) * 2048 + (uint32_t)row * 16;
     uint32_t a_stage = 0, a_phase = 0, t_stage = 0, t_phase = 0;
+    int tr = 0;
+    const bool tracer = warp == 0 && lane == 0;
+    (void)tr; (void)tracer;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int sp = w / p.m_units;
       const int c0 = sp * chunks_per_split;
@@ -370,18 +382,23 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       // in pair mode the tile stream alternates between the two m-tiles of the work item, chunk by chunk
       for (int sc = (c1 - c0) * tiles_per_item; sc > 0; --sc) {
         mbar_wait_a(full_t + 8 * t_stage, t_phase);
+        if (tracer) LMDEC_STAMP(0, tr);   // tile arrived
         const uint32_t src = smem_t_a + t_stage * kTileBytes + my_off;
         uint4 raw[kKbPerProducer / 2];
 #pragma unroll
         for (int i = 0; i < kKbPerProducer / 2; ++i) raw[i] = lds128(src + i * 2048);
         mbar_wait_a(empty_a + 8 * a_stage, a_phase ^ 1);
+        if (tracer) LMDEC_STAMP(1, tr);   // A stage free
         tc_fence_after_sync();
         const uint32_t a_addr = lane_addr + kARingCol0 + a_stage * a_stage_cols;
         if (p.has_missing)
           produce_chunk<true>(raw, a_addr, half);
         else
           produce_chunk<false>(raw, a_addr, half);
+        if (tracer) LMDEC_STAMP(2, tr);   // decode + tcgen05.st issued
         tmem_wait_st();
+        if (tracer) LMDEC_STAMP(3, tr);   // stores complete
+        ++tr;
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {
@@ -466,6 +483,8 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       const uint32_t kb_step = (uint32_t)(2 * N);  // one K-block of the image, in 16-byte units
       uint32_t a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       uint32_t tile_no = 0;
+      int tr = 0;
+      (void)tr;
       const bool all_kb = p.has_missing || p.pair == kPairT;  // this issuer runs all 8 K-blocks of a chunk (else parity me)
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
         const int sp = w / p.m_units;
@@ -485,6 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
               const bool mine = quad ? (t == my_tile) : (p.pair != kPairT || t == me);
               if (mine) {
                 mbar_wait_a(full_a + 8 * a_stage, a_phase);
+                if (issuer == 0 && lane == 0) LMDEC_STAMP(4, tr);   // A stage full seen by issuer 0
                 tc_fence_after_sync();
                 const uint32_t slot = p.pair ? (uint32_t)t : set;
                 const uint32_t d_addr = tbase + (p.pair == kPairT ? slot : slot * 2 + me) * acc_w;
@@ -504,6 +524,8 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
                   umma_commit_a(empty_a + 8 * a_stage);
                 }
                 __syncwarp();
+                if (issuer == 0 && lane == 0) LMDEC_STAMP(5, tr);   // MMAs issued + committed
+                if (issuer == 0) ++tr;
                 accumulate[t] = 1;
               }
               if (++a_stage == (uint32_t)a_stages) {

@@ -1049,6 +1049,12 @@ int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const in
 }
 
 // ---- CUDA-event timing of the dominant kernel (bench.py's roofline): events are recorded on the launching stream
+#ifdef LMDEC_TRACE
+int lmdec_trace_read(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 8 * kTraceChunks);
+}
+#endif
+
 void lmdec_set_pair_mode(int on) {
   g_pair_mode = on != 0;
   if (on > 1) g_pair_min_chunks = on;  // values > 1 also set the shortest contraction (in 256-wide chunks) that pairs
