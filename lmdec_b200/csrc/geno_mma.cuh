@@ -27,11 +27,15 @@
 
 namespace lmdec {
 
-#ifndef LMDEC_PRODUCER_WARPS
-#define LMDEC_PRODUCER_WARPS 8
-#endif
-constexpr int kProducerWarps = LMDEC_PRODUCER_WARPS;          // 8 or 16 (4 lane quarters x 2 or 4 K-block groups)
-constexpr int kKbPerProducer = 32 / kProducerWarps;           // K-blocks of a chunk decoded by one producer thread
+// 8 producer warps in kGroups groups (kernel template parameter):
+//   1 group : warps 0-3 decode K-blocks 0-3 and warps 4-7 K-blocks 4-7 of EVERY tile-chunk (32 bytes of a row per thread)
+//   2 groups: warps 0-3 and warps 4-7 take ALTERNATE tile-chunks, all 8 K-blocks each (64 bytes of a row per thread).
+// The per-iteration latency chain of a producer (barrier waits, fences, arrives: ~500 cycles,
+// profiles/r01/pipeline_trace.txt) is then paid once per 64 bytes instead of once per 32.  Two groups win without
+// missing data (deep A ring: 61,000 x 800,000 K=30 -7 %); with missing data the ring has two stages, each group would
+// own one and serialise with its MMAs (+17 % on A t), so one group is used there.  (A run-time switch inside one
+// kernel cost 6 %: the producer loop is that sensitive to extra instructions.)
+constexpr int kProducerWarps = 8;
 constexpr int kTileLoaderWarp = kProducerWarps;
 constexpr int kIssuerWarp0 = kProducerWarps + 1;
 #ifndef LMDEC_ISSUER_WARPS
@@ -126,18 +130,18 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
-template <bool kMiss>
-__device__ __forceinline__ void produce_chunk(const uint4 (&raw)[kKbPerProducer / 2], uint32_t a_stage_addr, int part) {
-  // this thread's bytes = K-blocks kKbPerProducer*part .. +kKbPerProducer of the chunk; raw[i] = 64 codes = 2 K-blocks
+template <bool kMiss, int KB>
+__device__ __forceinline__ void produce_chunk(const uint4 (&raw)[KB / 2], uint32_t a_stage_addr, int kb0) {
+  // this thread's bytes = K-blocks kb0 .. kb0 + KB of the chunk; raw[i] = 64 codes = 2 K-blocks
 #pragma unroll
-  for (int i = 0; i < kKbPerProducer / 2; ++i) {
+  for (int i = 0; i < KB / 2; ++i) {
     const uint32_t regs[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       uint32_t v[8], m[8];
       decode16<kMiss>(regs[2 * j], v, m);
       decode16<kMiss>(regs[2 * j + 1], v + 4, m + 4);
-      const int kb = kKbPerProducer * part + 2 * i + j;
+      const int kb = kb0 + 2 * i + j;
       tmem_st8(a_stage_addr + kb * 8, v);
       if (kMiss) tmem_st8(a_stage_addr + 64 + kb * 8, m);
     }
@@ -303,7 +307,10 @@ __device__ __forceinline__ void epilogue_dispatch(const GenoMmaParams& p, uint32
 #undef LMDEC_EPI
 }
 
+template <int kGroups>
 __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaParams p) {
+  constexpr int kGroupWarps = kProducerWarps / kGroups;   // producer warps per tile-chunk
+  constexpr int kKb = 32 / kGroupWarps;                   // K-blocks of a chunk decoded by one producer thread
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[kNumBars];  // see the kBar* offsets: all rings' full / empty barriers
   __shared__ uint32_t tmem_base_s;
@@ -340,10 +347,10 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   if (tid == 32) {
     for (int i = 0; i < kMaxTileStages; ++i) {
       mbar_init(&bars[kBarFullT + i], 1);
-      mbar_init(&bars[kBarEmptyT + i], kProducerWarps);
+      mbar_init(&bars[kBarEmptyT + i], kGroupWarps);
     }
     for (int i = 0; i < kMaxAStages; ++i) {
-      mbar_init(&bars[kBarFullA + i], kProducerWarps);
+      mbar_init(&bars[kBarFullA + i], kGroupWarps);
       mbar_init(&bars[kBarEmptyA + i], p.pair == kPairT ? 1 : 2);
     }
     for (int i = 0; i < kMaxBStages; ++i) {
@@ -367,10 +374,12 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
 
   if (warp < kProducerWarps) {
     // ------------------------------------------------------------------ producers
-    const int q = warp & 3, half = warp >> 2;
+    const int group = warp / kGroupWarps, lw = warp % kGroupWarps;
+    const int q = lw & 3, half = lw >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
-    const uint32_t my_off = (uint32_t)((kKbPerProducer / 2) * half) * 2048 + (uint32_t)row * 16;
+    const uint32_t my_off = (uint32_t)((kKb / 2) * half) * 2048 + (uint32_t)row * 16;
+    uint32_t gsc = 0;   // running tile-chunk count: with two groups, group g takes those of parity g
     uint32_t a_stage = 0, a_phase = 0, t_stage = 0, t_phase = 0;
     int tr = 0;
     const bool tracer = warp == 0 && lane == 0;
@@ -380,21 +389,32 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       const int c0 = sp * chunks_per_split;
       const int c1 = min(c0 + chunks_per_split, p.n_chunks);
       // in pair mode the tile stream alternates between the two m-tiles of the work item, chunk by chunk
-      for (int sc = (c1 - c0) * tiles_per_item; sc > 0; --sc) {
+      for (int sc = (c1 - c0) * tiles_per_item; sc > 0; --sc, ++gsc) {
+        if (kGroups == 2 && (gsc & 1) != (uint32_t)group) {   // the other group's tile-chunk: step the ring positions
+          if (++a_stage == (uint32_t)a_stages) {
+            a_stage = 0;
+            a_phase ^= 1;
+          }
+          if (++t_stage == (uint32_t)p.tile_stages) {
+            t_stage = 0;
+            t_phase ^= 1;
+          }
+          continue;
+        }
         mbar_wait_a(full_t + 8 * t_stage, t_phase);
         if (tracer) LMDEC_STAMP(0, tr);   // tile arrived
         const uint32_t src = smem_t_a + t_stage * kTileBytes + my_off;
-        uint4 raw[kKbPerProducer / 2];
+        uint4 raw[kKb / 2];
 #pragma unroll
-        for (int i = 0; i < kKbPerProducer / 2; ++i) raw[i] = lds128(src + i * 2048);
+        for (int i = 0; i < kKb / 2; ++i) raw[i] = lds128(src + i * 2048);
         mbar_wait_a(empty_a + 8 * a_stage, a_phase ^ 1);
         if (tracer) LMDEC_STAMP(1, tr);   // A stage free
         tc_fence_after_sync();
         const uint32_t a_addr = lane_addr + kARingCol0 + a_stage * a_stage_cols;
         if (p.has_missing)
-          produce_chunk<true>(raw, a_addr, half);
+          produce_chunk<true, kKb>(raw, a_addr, kKb * half);
         else
-          produce_chunk<false>(raw, a_addr, half);
+          produce_chunk<false, kKb>(raw, a_addr, kKb * half);
         if (tracer) LMDEC_STAMP(2, tr);   // decode + tcgen05.st issued
         tmem_wait_st();
         if (tracer) LMDEC_STAMP(3, tr);   // stores complete

@@ -33,6 +33,7 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_mma_events;
 static bool g_mma_timing = false;
 static int g_sm_reserve = 0;
 static int g_pair_min_chunks = 64;
+static int g_prod_groups2 = 1;
 static int g_pair_mode = 1;   // lmdec_set_pair_mode: 0 disables the two-tiles-per-B-stage schedule (A/B tests)  // SMs left free for concurrently running collectives (row-sharded runs)
 
 namespace lmdec {
@@ -829,7 +830,9 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
   const size_t smem = (size_t)tile_stages * kTileBytes + b_stages * stage_bytes + scratch;
   cudaStream_t st = (cudaStream_t)stream;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(geno_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(geno_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(geno_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
     if (e != cudaSuccess) return fail("lmdec_geno_matmul: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -846,7 +849,11 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
     cudaEventCreate(&ev1);
     cudaEventRecord(ev0, st);
   }
-  geno_mma_kernel<<<grid, kThreads, smem, st>>>(p);
+  // producer grouping (see geno_mma.cuh): two groups without missing data, one with
+  if (!has_missing && g_prod_groups2)
+    geno_mma_kernel<2><<<grid, kThreads, smem, st>>>(p);
+  else
+    geno_mma_kernel<1><<<grid, kThreads, smem, st>>>(p);
   if (g_mma_timing) {
     cudaEventRecord(ev1, st);
     g_mma_events.emplace_back(ev0, ev1);
