@@ -499,9 +499,17 @@ __global__ void __launch_bounds__(128) chol_whiten_kernel(const double* __restri
   if (n_partials > 0) {
     const int stride = K * K + K;
     for (int i = t; i < K * K; i += blockDim.x) {
-      double a = 0.0;
-      for (int b = 0; b < n_partials; ++b) a += G[(size_t)b * stride + i];
-      g_out[i] = a;
+      // four loads in flight; the partial sums are always combined in the same order (deterministic)
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int b = 0;
+      for (; b + 4 <= n_partials; b += 4) {
+        a0 += G[(size_t)b * stride + i];
+        a1 += G[(size_t)(b + 1) * stride + i];
+        a2 += G[(size_t)(b + 2) * stride + i];
+        a3 += G[(size_t)(b + 3) * stride + i];
+      }
+      for (; b < n_partials; ++b) a0 += G[(size_t)b * stride + i];
+      g_out[i] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
     G = g_out;
@@ -1012,7 +1020,17 @@ __global__ void qr_pack_kernel(const double* __restrict__ r1, const double* __re
                                const double* __restrict__ g2, const int* __restrict__ f1, const int* __restrict__ f2,
                                int K, double* __restrict__ packed) {
   __shared__ double red[128];
+  extern __shared__ double qsm[];        // r1 | r2 staged in shared memory when they fit (K <= 64)
   const int t = threadIdx.x;
+  if (K <= 64) {
+    for (int i = t; i < K * K; i += blockDim.x) {
+      qsm[i] = r1[i];
+      qsm[K * K + i] = r2[i];
+    }
+    __syncthreads();
+    r1 = qsm;
+    r2 = qsm + K * K;
+  }
   double dev = 0.0;
   for (int i = t; i < K * K; i += blockDim.x) {
     const int a = i / K, b = i - a * K;
@@ -1051,7 +1069,13 @@ int lmdec_gram_chol(const double* X, int64_t ldx, int64_t m, int K, double rank_
 int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const int* flag1, const int* flag2, int K,
                   double* packed, void* stream) {
   if (K < 1 || K > 128) return fail("lmdec_qr_pack: K out of range (1..128)");
-  qr_pack_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(r1, r2, g2, flag1, flag2, K, packed);
+  const size_t smem = K <= 64 ? (size_t)2 * K * K * sizeof(double) : 0;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(qr_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + 1024);
+    attr_set = true;
+  }
+  qr_pack_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(r1, r2, g2, flag1, flag2, K, packed);
   return check_launch("lmdec_qr_pack");
 }
 
