@@ -6,6 +6,8 @@ plain library GEMMs (cuBLAS through torch) in float64.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -53,7 +55,7 @@ class DenseOperator:
     # A = A_hi + A_lo, x = x_hi + x_lo on the TF32 tensor cores (A_hi x_hi + A_lo x_hi + A_hi x_lo: fp32-level accuracy).
     # Measured on configs[4] (1M x 4k, K = 110) the three skinny cuBLAS TF32 GEMMs are slower than the fp32 one (58 vs
     # 47 ms per iteration), so it stays opt-in until the dense path gets its own tcgen05 kernel.
-    f32_mode = __import__("os").environ.get("LMDEC_DENSE_F32", "fp32")
+    f32_mode = os.environ.get("LMDEC_DENSE_F32", "fp32")
 
     def _split(self):
         if getattr(self, "_hi", None) is None:

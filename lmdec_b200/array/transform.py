@@ -1,10 +1,9 @@
 """u / s shaping for rmse (reference lmdec/array/transform.py:8-78)."""
 from __future__ import annotations
 
-import numpy as np
 import torch
 
-from ..device import DeviceArray, as_tensor
+from ..device import as_tensor
 
 
 def acc_format_svd(u, s, array_shape, square: bool = True):

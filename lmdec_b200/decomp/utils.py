@@ -4,10 +4,9 @@ from __future__ import annotations
 from collections import namedtuple
 from typing import Optional
 
-import numpy as np
 import torch
 
-from ..device import F64, DeviceArray, as_tensor, require_cuda
+from ..device import DeviceArray, as_tensor
 from ..store import GenotypeOperator, GenotypeStore
 
 PowerMethodSummary = namedtuple("PowerMethodSummary", ["time", "acc", "iter"])

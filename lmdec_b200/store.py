@@ -18,7 +18,7 @@ The two big products run exactly (int64) on the tensor cores: the float64 operan
 from __future__ import annotations
 
 import ctypes as C
-import math
+import os
 from typing import Optional
 
 import numpy as np
@@ -29,8 +29,6 @@ from .device import F64, DeviceArray, as_tensor, require_cuda
 
 _DTYPE_CODE = {torch.int8: 0, torch.uint8: 1, torch.float32: 2, torch.float64: 3}
 
-
-_REDUCE_DTYPE = {"f32": torch.float32, "f64": torch.float64}[__import__("os").environ.get("LMDEC_REDUCE_DTYPE", "f32")]
 
 # bench.py sets this to a list to time the dominant kernel with CUDA events on the launching stream
 KERNEL_EVENTS = None
@@ -387,7 +385,7 @@ class GenotypeOperator:
         always float64.  Row-sharded: float32 -- half the NVLink bytes of the all-reduce, and its 24-bit mantissa is finer
         than the 22-bit fixed point t is quantised to on its next use (2 x B200: 1.28 vs 1.41 ms per iteration).  Single
         GPU: float64 (float32 -> float64 conversions in the operand kernels cost more than the halved reads save)."""
-        env = __import__("os").environ.get("LMDEC_WIDE_DTYPE")
+        env = os.environ.get("LMDEC_WIDE_DTYPE")
         if env:
             return {"f32": torch.float32, "f64": torch.float64}[env]
         return torch.float32 if self.store.group is not None else torch.float64
@@ -421,12 +419,12 @@ class GenotypeOperator:
         K = y.shape[1]
         w = torch.empty((st.p, K), dtype=out_dtype, device=st.device)
         n_tiles = (st.p + 127) // 128
-        parts = max(1, min(int(getattr(st, "reduce_parts", 0) or __import__("os").environ.get("LMDEC_REDUCE_PARTS", "1")),
+        parts = max(1, min(int(getattr(st, "reduce_parts", 0) or os.environ.get("LMDEC_REDUCE_PARTS", "1")),
                            n_tiles))
         bounds = [min(st.p, (n_tiles * i // parts) * 128) for i in range(parts)] + [st.p]
         pending = []
         if parts > 1:
-            st.lib.lmdec_set_sm_reserve(int(__import__("os").environ.get("LMDEC_SM_RESERVE", "16")))
+            st.lib.lmdec_set_sm_reserve(int(os.environ.get("LMDEC_SM_RESERVE", "16")))
         for i in range(parts):
             m0, m1 = bounds[i], bounds[i + 1]
             if m1 <= m0:
