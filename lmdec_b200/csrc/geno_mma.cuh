@@ -215,6 +215,7 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
         fdst32 = (float*)p.fz.out + m * p.fz.ldo;
       }
       const double row_a3 = (row_a - 3.0) * row_scale;  // MODE 1: out = rs*(acc0 - 3 acc1) + rs*ra*acc1
+      const float rs32 = (float)row_scale, ra32 = (float)row_a3, rsh32 = (float)row_shift;
       if (g_first >= n_groups && t == tiles_per_item - 1) {
         // no column group for this warp (K <= 8 with two warps per quarter): it still takes part in the hand-back
         tc_fence_before_sync();
@@ -261,13 +262,16 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
             if (OUT == kOutFused) {
               // integer plane combine (ALU pipe) and ONE int64 -> float64 conversion per accumulator: the fp64 /
               // conversion pipe is the scarce one in this epilogue (stall_math in profiles/r01)
-              double v = (double)planes_to_int64<P>(r0 + kk * P) * row_scale;
-              if (MODE == 1) v = fma((double)planes_to_int64<P>(r1 + kk * P), row_a3, v);
-              v = fma(v, fz_col[k], row_shift * fz_col[128 + k]);
-              if (p.fz.out_f32)
-                fdst32[k] = (float)v;
-              else
-                fdst[k] = v;
+              if (p.fz.out_f32) {
+                // float32 output: the whole finalize runs on the fp32 pipe (one rounding more than the store itself)
+                float v = (float)planes_to_int64<P>(r0 + kk * P) * rs32;
+                if (MODE == 1) v = fmaf((float)planes_to_int64<P>(r1 + kk * P), ra32, v);
+                fdst32[k] = fmaf(v, (float)fz_col[k], rsh32 * (float)fz_col[128 + k]);
+              } else {
+                double v = (double)planes_to_int64<P>(r0 + kk * P) * row_scale;
+                if (MODE == 1) v = fma((double)planes_to_int64<P>(r1 + kk * P), row_a3, v);
+                fdst[k] = fma(v, fz_col[k], row_shift * fz_col[128 + k]);
+              }
             } else {
               const long long acc = planes_to_int64<P>(r0 + kk * P);
               if (OUT == kOutAtomic)
