@@ -58,6 +58,11 @@ def cpu_step_throughput(steps: int, warmup: int, budget_s: float = 25.0):
         return g
 
     cores = os.cpu_count() or 1
+    try:   # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host core it can use
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     p_s = 40_000
     g = synth_genotypes(N_ROWS, p_s, MISS, seed=0, dtype=np.float32)
     op = oracle.make_snp_array(g, std_method="binom")
