@@ -155,6 +155,13 @@ int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, do
  * factorisation kernel) and its Cholesky whitening, two launches.  G receives X^T X.  work: lmdec_gram_work_doubles. */
 int lmdec_gram_chol(const double* X, int64_t ldx, int64_t m, int K, double rank_tol, double* G, double* r_inv,
                     double* r, int* flag, double* work, void* stream);
+/* Whole CholeskyQR2 of a small local iterate (K <= 32, n*K <= lmdec_cholqr2_small_max_elems()) in one launch of one
+ * 8-CTA cluster (row slices stay in shared memory, Gram partials meet through distributed shared memory; replaces the
+ * reference's tsqr of the n x K iterate, lmdec/decomp/iter_methods.py:478-479): Q = orthonormalised X,
+ * packed = [r2 r1 (K*K) | flag1 | flag2 | max|Q1^T Q1 - I|].  */
+int64_t lmdec_cholqr2_small_max_elems(void);
+int lmdec_cholqr2_small(const double* X, int64_t ldx, int64_t n, int K, double rank_tol, double* Q, int64_t ldq,
+                        double* packed, void* stream);
 /* packed[0..K*K) = r2 r1, then flag1, flag2, max|g2 - I|: what the host reads back from one CholeskyQR2. */
 int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const int* flag1, const int* flag2, int K,
                   double* packed, void* stream);

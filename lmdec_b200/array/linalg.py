@@ -8,10 +8,12 @@ the rank-revealing fallback had to be taken.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
-from ..device import F64, chol_whiten, gram, gram_chol, qr_pack
+from ..device import F64, chol_whiten, cholqr2_small, cholqr2_small_fits, gram, gram_chol, qr_pack
 
 
 def _allreduce(t: torch.Tensor, group):
@@ -90,6 +92,7 @@ def orthonormalize(x: torch.Tensor, group=None, seed: int = 0, gram_fn=None):
 
 
 _SIDE = {}
+_SMALL_QR = os.environ.get("LMDEC_SMALL_QR", "1") != "0"   # single-launch CholeskyQR2 for small iterates (A/B switch)
 
 
 def _side_stream(device):
@@ -130,6 +133,9 @@ def orthonormalize_begin(x: torch.Tensor, group=None) -> _PendingQR:
     """Enqueue CholeskyQR2 entirely on the device (both K x K factorizations included) and return without syncing, so
     the caller can queue the next products behind it before asking for r."""
     K = x.shape[1]
+    if group is None and x.dtype == F64 and _SMALL_QR and cholqr2_small_fits(x.shape[0], K):
+        q, packed = cholqr2_small(x)                   # one launch for the whole CholeskyQR2
+        return _PendingQR(q, packed, K)
     if group is None:
         _, ri1, r1, f1 = gram_chol(x)                  # 2 launches per pass, nothing else
         q1 = x @ ri1

@@ -1,6 +1,7 @@
 // C-ABI implementation (include/lmdec_b200.h): tile-store kernels, operand quantisation, the tcgen05 product, and the
 // small fp64 reductions of the power iteration.  sm_100a only; there is no CPU path in this library.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -563,6 +564,224 @@ __global__ void __launch_bounds__(128) chol_whiten_kernel(const double* __restri
   if (t == 0) *flag = bad;
 }
 
+
+// ---- single-launch CholeskyQR2 for small iterates (the n x K side of the power iteration)
+constexpr int kCqrThreads = 512;
+constexpr int kCqrCluster = 8;          // CTAs of one cluster share the row range; Gram partials meet through DSMEM
+constexpr int kCqrSliceDoubles = 8192;  // per-CTA row slice kept in shared memory (x2: input and first-pass output)
+
+// Cholesky whitening of the K x K Gram matrix G (shared memory) by the whole block, one matrix element per thread
+// (two when K*K > 512) held in a register; each elimination step costs one __syncthreads:
+//   G -> unit-diagonal scaling -> right-looking Cholesky -> right-looking triangular inverse
+//   -> r = (L diag(d))^T, r_inv = r^-1 (both upper, shared memory).
+// Same algorithm and failure flag as chol_whiten_kernel (pivot below rank_tol, non-finite or non-positive diagonal).
+// scratch: Lw [K*K] working columns, Lf [K*K] final factor, vec [4*K] (d | 1/L_jj | two row buffers).
+__device__ int block_chol(const double* __restrict__ G, int K, double rank_tol, double* __restrict__ Lw,
+                          double* __restrict__ Lf, double* __restrict__ vec, double* __restrict__ r_inv,
+                          double* __restrict__ r) {
+  const int t = threadIdx.x, kk = K * K;
+  double* dvec = vec;
+  double* invd = vec + K;
+  double* xrow = vec + 2 * K;
+  int bad = 0;
+  if (t < K) {
+    const double dg = G[t * K + t];
+    const bool ok = dg > 0.0 && isfinite(dg);
+    dvec[t] = ok ? sqrt(dg) : 1.0;
+    if (!ok) bad = 1;
+  }
+  __syncthreads();
+  int ei[2], ec[2];
+  bool act[2];
+  double v[2], lf[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int e = t + u * kCqrThreads;
+    act[u] = e < kk;
+    ei[u] = act[u] ? e / K : 0;
+    ec[u] = act[u] ? e - ei[u] * K : 0;
+    v[u] = 0.0;
+    lf[u] = 0.0;
+    if (act[u]) {
+      v[u] = 0.5 * (G[ei[u] * K + ec[u]] + G[ec[u] * K + ei[u]]) / (dvec[ei[u]] * dvec[ec[u]]);
+      if (!isfinite(v[u])) bad = 1;
+      Lw[e] = v[u];
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < K; ++j) {
+    const double piv = Lw[j * K + j];
+    if (!(piv >= rank_tol)) bad = 1;
+    const double pc = piv > rank_tol ? piv : rank_tol;
+    const double x = rsqrt(pc);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!act[u]) continue;
+      const int i = ei[u], c = ec[u];
+      if (c == j) {
+        lf[u] = i > j ? v[u] * x : (i == j ? pc * x : 0.0);
+        if (i == j) invd[j] = x;
+      } else if (c > j && i >= c) {
+        v[u] -= (Lw[i * K + j] * x) * (Lw[c * K + j] * x);
+        if (c == j + 1) Lw[i * K + c] = v[u];     // the next step's column
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+    if (act[u]) Lf[t + u * kCqrThreads] = lf[u];
+  __syncthreads();
+  // X = L^-1: element (i, c) accumulates delta_ic - sum_{m < i} L[i][m] X[m][c]; row m is final once steps < m ran
+  double acc[2], xf[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    acc[u] = (act[u] && ei[u] == ec[u]) ? 1.0 : 0.0;
+    xf[u] = 0.0;
+  }
+  for (int m = 0; m < K; ++m) {
+    double* xr = xrow + (m & 1) * K;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (act[u] && ei[u] == m) {
+        xf[u] = acc[u] * invd[m];
+        xr[ec[u]] = xf[u];
+      }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (act[u] && ei[u] > m) acc[u] -= Lf[ei[u] * K + m] * xr[ec[u]];
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (!act[u]) continue;
+    const int i = ei[u], c = ec[u];
+    r[c * K + i] = (c <= i) ? lf[u] * dvec[i] : 0.0;         // r[a][b] = L[b][a] d[b]
+    r_inv[c * K + i] = (c <= i) ? xf[u] / dvec[c] : 0.0;     // r_inv[a][b] = X[b][a] / d[a]
+  }
+  return __syncthreads_or(bad);
+}
+
+// Gram matrix of this CTA's row slice (shared memory) -> part[K*K]; upper triangle computed once, mirrored.
+__device__ void cqr_gram_local(const double* __restrict__ sl, int rows, int K, double* __restrict__ pacc,
+                               double* __restrict__ part) {
+  const int t = threadIdx.x;
+  const int npairs = K * (K + 1) / 2;
+  const int H = kCqrThreads / npairs >= 2 ? 2 : 1;       // row halves when the thread count allows
+  const int per = (rows + H - 1) / H;
+  for (int o = t; o < npairs * H; o += kCqrThreads) {
+    const int h = o / npairs;
+    int e = 0, rem = o - h * npairs;
+    while (rem >= K - e) { rem -= K - e; ++e; }
+    const int f = e + rem;
+    const int lo = h * per, hi = min(rows, lo + per);
+    double a0 = 0.0, a1 = 0.0;
+    int r = lo;
+    for (; r + 1 < hi; r += 2) {
+      a0 += sl[r * K + e] * sl[r * K + f];
+      a1 += sl[(r + 1) * K + e] * sl[(r + 1) * K + f];
+    }
+    if (r < hi) a0 += sl[r * K + e] * sl[r * K + f];
+    pacc[o] = a0 + a1;
+  }
+  __syncthreads();
+  for (int i = t; i < K * K; i += kCqrThreads) {
+    int a = i / K, b = i - a * K;
+    if (a > b) { const int w = a; a = b; b = w; }
+    const int pr = a * K - a * (a - 1) / 2 + (b - a);
+    part[i] = H == 2 ? pacc[pr] + pacc[npairs + pr] : pacc[pr];
+  }
+}
+
+// out[r][b] = sum_{a <= b} in[r][a] r_inv[a][b]; one thread per element
+__device__ void cqr_apply(const double* __restrict__ in, int rows, int K, const double* __restrict__ r_inv,
+                          double* __restrict__ out, int64_t ldo) {
+  for (int i = threadIdx.x; i < rows * K; i += kCqrThreads) {
+    const int r = i / K, b = i - r * K;
+    const double* row = in + r * K;
+    double acc = 0.0;
+    for (int a = 0; a <= b; ++a) acc += row[a] * r_inv[a * K + b];
+    out[(int64_t)r * ldo + b] = acc;
+  }
+}
+
+// CholeskyQR2 of a small iterate X [n][K] in ONE launch of one 8-CTA cluster: each CTA keeps its row slice in shared
+// memory for both passes, the K x K Gram partials are summed through distributed shared memory in a fixed order
+// (every CTA gets the same bits), every CTA factorises redundantly and applies r^-1 to its own rows.
+// packed = [r2 r1 | flag1 | flag2 | max|Q1^T Q1 - I|] as qr_pack_kernel writes it.
+__global__ void __cluster_dims__(kCqrCluster, 1, 1) __launch_bounds__(kCqrThreads)
+    cholqr2_small_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int K, int per, double rank_tol,
+                         double* __restrict__ Q, int64_t ldq, double* __restrict__ packed) {
+  extern __shared__ double cqr_sm[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int t = threadIdx.x;
+  const int kk = K * K;
+  double* buf0 = cqr_sm;                  // [per][K] input slice
+  double* buf1 = buf0 + (size_t)per * K;  // [per][K] first-pass output
+  double* part1 = buf1 + (size_t)per * K; // Gram partial of pass 1 (read by the peers)
+  double* part2 = part1 + kk;
+  double* pacc = part2 + kk;              // [2][K(K+1)/2] <= kk + K
+  double* G = pacc + kk + K;
+  double* Lsm = G + kk;
+  double* Lf = Lsm + kk;
+  double* vec = Lf + kk;                  // [4][K]
+  double* ri = vec + 4 * K;
+  double* r1 = ri + kk;
+  double* r2 = r1 + kk;
+  __shared__ int flags[2];
+  __shared__ double red[kCqrThreads / 32];
+  const int64_t row0 = (int64_t)rank * per;
+  const int rows = (int)max((int64_t)0, min((int64_t)per, n - row0));
+  for (int i = t; i < rows * K; i += kCqrThreads) {
+    const int r = i / K, c = i - r * K;
+    buf0[i] = X[(row0 + r) * ldx + c];
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 2; ++pass) {
+    double* part = pass ? part2 : part1;
+    cqr_gram_local(pass ? buf1 : buf0, rows, K, pacc, part);
+    cluster.sync();
+    for (int i = t; i < kk; i += kCqrThreads) {
+      double acc = 0.0;
+      for (int c = 0; c < kCqrCluster; ++c) acc += cluster.map_shared_rank(part, c)[i];
+      G[i] = acc;
+    }
+    __syncthreads();
+    if (pass == 1) {   // deviation of the second Gram matrix from the identity (health check of the first pass)
+      double dev = 0.0;
+      for (int i = t; i < kk; i += kCqrThreads) {
+        const double g = G[i] - ((i / K) == (i % K) ? 1.0 : 0.0);
+        dev = fmax(dev, g == g ? fabs(g) : INFINITY);
+      }
+      for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+      if ((t & 31) == 0) red[t >> 5] = dev;
+    }
+    const int f = block_chol(G, K, rank_tol, Lsm, Lf, vec, ri, pass ? r2 : r1);
+    if (t == 0) flags[pass] = f;
+    if (pass == 0) cqr_apply(buf0, rows, K, ri, buf1, K);
+    else cqr_apply(buf1, rows, K, ri, Q + row0 * ldq, ldq);
+    __syncthreads();
+  }
+  if (rank == 0) {
+    for (int i = t; i < kk; i += kCqrThreads) {
+      const int a = i / K, b = i - a * K;
+      double acc = 0.0;
+      for (int c = a; c <= b; ++c) acc += r2[a * K + c] * r1[c * K + b];
+      packed[i] = acc;
+    }
+    if (t == 0) {
+      double m = 0.0;
+      for (int i = 0; i < kCqrThreads / 32; ++i) m = fmax(m, red[i]);
+      packed[kk] = (double)flags[0];
+      packed[kk + 1] = (double)flags[1];
+      packed[kk + 2] = m;
+    }
+  }
+  cluster.sync();   // peers may still be reading this CTA's part2
+}
+
 __global__ void qvals_kernel(const double* __restrict__ si, const double* __restrict__ sj, int k, int scale,
                              double* __restrict__ out) {
   double d = 0, a = 0, b = 0;
@@ -1064,6 +1283,25 @@ int lmdec_gram_chol(const double* X, int64_t ldx, int64_t m, int K, double rank_
   gram_partial_kernel<<<nb, 256, (size_t)kGramRows * K * sizeof(double), st>>>(X, ldx, nullptr, 0, m, K, work);
   chol_whiten_kernel<<<1, 128, (size_t)(2 * K * K + K) * sizeof(double), st>>>(work, K, rank_tol, r_inv, r, flag, nb, G);
   return check_launch("lmdec_gram_chol", 2);
+}
+
+int64_t lmdec_cholqr2_small_max_elems(void) { return (int64_t)kCqrCluster * kCqrSliceDoubles; }
+
+int lmdec_cholqr2_small(const double* X, int64_t ldx, int64_t n, int K, double rank_tol, double* Q, int64_t ldq,
+                        double* packed, void* stream) {
+  if (K < 1 || K > 32) return fail("lmdec_cholqr2_small: K out of range (1..32)");
+  if (n < 1 || Q == X) return fail("lmdec_cholqr2_small: needs n >= 1 and an output distinct from the input");
+  const int64_t per = (n + kCqrCluster - 1) / kCqrCluster;
+  if (per * K > kCqrSliceDoubles) return fail("lmdec_cholqr2_small: iterate too large (see lmdec_cholqr2_small_max_elems)");
+  const size_t smem = ((size_t)2 * per * K + 10 * K * K + 5 * K) * sizeof(double);
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(cholqr2_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    attr_set = true;
+  }
+  cholqr2_small_kernel<<<kCqrCluster, kCqrThreads, smem, (cudaStream_t)stream>>>(X, ldx, n, K, (int)per, rank_tol, Q,
+                                                                                 ldq, packed);
+  return check_launch("lmdec_cholqr2_small");
 }
 
 int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const int* flag1, const int* flag2, int K,

@@ -230,3 +230,20 @@ def qr_pack(r1, r2, g2, f1, f2) -> torch.Tensor:
     _capi.check(lib.lmdec_qr_pack(_capi.ptr(r1), _capi.ptr(r2), _capi.ptr(g2), _capi.ptr(f1), _capi.ptr(f2), K,
                                   _capi.ptr(packed), _capi.stream_ptr()), "lmdec_qr_pack")
     return packed
+
+
+def cholqr2_small_fits(n: int, K: int) -> bool:
+    per = -(-n // 8)
+    return K <= 32 and per * K * 8 <= _capi.load().lmdec_cholqr2_small_max_elems()
+
+
+def cholqr2_small(x: torch.Tensor, rank_tol: float = 1e-12):
+    """CholeskyQR2 of a small local iterate in one launch: (q, packed) with packed = [r | flag1 | flag2 | dev]."""
+    lib = _capi.load()
+    x = _rows(x)
+    n, K = x.shape
+    q = torch.empty((n, K), dtype=F64, device=x.device)
+    packed = torch.empty(K * K + 3, dtype=F64, device=x.device)
+    _capi.check(lib.lmdec_cholqr2_small(_capi.ptr(x), x.stride(0), n, K, float(rank_tol), _capi.ptr(q), K,
+                                        _capi.ptr(packed), _capi.stream_ptr()), "lmdec_cholqr2_small")
+    return q, packed

@@ -218,3 +218,47 @@ def test_recode_bed_matches_plink_code_map(cuda):
     cnt = torch.empty((n_var, 4), dtype=torch.int64, device=cuda)
     capi.check(lib.lmdec_code_counts(capi.ptr(store), n_var, n_samp, n_samp, capi.ptr(cnt), capi.stream_ptr()))
     assert int(cnt.sum().item()) == n_var * n_samp
+
+
+@pytest.mark.parametrize("n,K", [(2504, 20), (3, 2), (37, 1), (256, 32), (2048, 32), (5000, 13)])
+def test_cholqr2_small_single_launch(cuda, n, K):
+    """One-cluster CholeskyQR2 == the general multi-launch path: Q^T Q = I, Q R = X, R upper with positive diagonal."""
+    import torch
+    from lmdec_b200.device import cholqr2_small, cholqr2_small_fits
+    assert cholqr2_small_fits(n, K)
+    rng = np.random.default_rng(n * 31 + K)
+    x = rng.standard_normal((n, K)) @ (np.eye(K) + 0.3 * rng.standard_normal((K, K))) * np.logspace(0, 3, K)
+    if n < K:
+        pytest.skip("wide iterate")
+    xd = torch.from_numpy(np.pad(x, ((0, 0), (0, 3)))).to(cuda)[:, :K]      # strided rows (ldx = K + 3)
+    q, packed = cholqr2_small(xd)
+    q, packed = q.cpu().numpy(), packed.cpu().numpy()
+    r = packed[:K * K].reshape(K, K)
+    assert packed[K * K] == 0 and packed[K * K + 1] == 0 and packed[K * K + 2] < 1e-6
+    np.testing.assert_allclose(q.T @ q, np.eye(K), atol=1e-13)
+    np.testing.assert_allclose(q @ r, x, rtol=0, atol=1e-12 * np.abs(x).max())
+    assert np.allclose(r, np.triu(r)) and (np.diag(r) > 0).all()
+    qn, rn = np.linalg.qr(x)
+    sgn = np.sign(np.diag(rn))
+    np.testing.assert_allclose(r, rn * sgn[:, None], rtol=1e-9, atol=1e-10 * np.abs(rn).max())
+
+
+def test_cholqr2_small_flags_rank_deficiency(cuda):
+    import torch
+    from lmdec_b200.device import cholqr2_small
+    from lmdec_b200.array.linalg import orthonormalize
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((500, 6))
+    x[:, 4] = x[:, 1]
+    xd = torch.from_numpy(x).to(cuda)
+    _, packed = cholqr2_small(xd)
+    packed = packed.cpu().numpy()
+    assert packed[36] != 0 or packed[37] != 0 or not packed[38] < 1e-2
+    q, r = orthonormalize(xd)                       # the host fallback takes over
+    q = q.cpu().numpy()
+    np.testing.assert_allclose(q.T @ q, np.eye(6), atol=1e-10)
+    np.testing.assert_allclose(q @ r, x, atol=1e-10)
+    xd[7, 2] = float("nan")
+    _, packed = cholqr2_small(xd)
+    packed = packed.cpu().numpy()
+    assert packed[36] != 0 or packed[37] != 0 or not packed[38] < 1e-2
