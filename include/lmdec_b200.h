@@ -136,6 +136,11 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
  * previous call are reused (several output row ranges of the same product, e.g. to pipeline an all-reduce);
  * bit 2 = B is float32 (else float64); bit 3 = out is float32 (else float64).  The p x K side of the iteration is
  * carried in float32 (24-bit mantissa > the 22-bit fixed point it is quantised to), the n x K side in float64.
+ * bit 4 (transpose = 1 only) = also leave in `work` the column statistics of `out` taken as the operand of the A.dot
+ * that follows in the power iteration (x = A (A^T q), iter_methods.py:383): the tensor-core epilogue reduces them while
+ * it writes `out` (K <= 32, float64 out, unsplit contraction; otherwise one extra pass over out);  bit 5 (transpose = 0
+ * only) = B is that `out` (all m_limit rows of it = this call's kd_limit, unmodified, same K, same `work`): the pass
+ * over B for its statistics is skipped.
  * Steps: column statistics of B (max for the fixed-point scale, weighted column sum for the rank-1 term), plane
  * quantisation, lmdec_geno_matmul, lmdec_finalize.  */
 int64_t lmdec_apply_work_doubles(int K);

@@ -69,6 +69,11 @@ struct FusedFinalize {
   void* out;      // float64, or float32 when out_f32
   long long ldo;
   int out_f32;
+  // optional (float64 out, K <= 32): column statistics of the OUTPUT taken as the operand of the following A.dot --
+  // per-CTA partials [gridDim.x][3][K] = max|out rowscale|, max|out rowscale rowa|, sum rowshift out (the layout
+  // colstats_partial_kernel writes) and the CTA count, so the next product needs no pass over its operand for them
+  double* stats_partial;
+  double* stats_nblocks;
 };
 
 #ifdef LMDEC_TRACE
@@ -103,6 +108,8 @@ struct GenoMmaParams {
   int a_stages;            // stages of the decoded-A ring: (512 - a_ring_col0) / (128 with missing data, else 64)
   int pair;                // 0: one m-tile per work item; 1/2/3: TWO m-tiles share every B stage (kPairM/E/T)
   int m_units;             // work items per split: m_tiles, or ceil(m_tiles / 2) in pair mode
+  int stats_off;           // byte offset of the statistics accumulators in dynamic shared memory (fuse == 2)
+  int stats_cols;          // column slots per epilogue thread
   int fuse;                // write the finalized float64 result from the epilogue (never with atomics)
   FusedFinalize fz;
 };
@@ -152,7 +159,11 @@ __device__ __forceinline__ void produce_chunk(const uint4 (&raw)[KB / 2], uint32
 // planes of 8 consecutive outputs are 8*P consecutive columns: everything stays in registers, indices are compile-time.
 // MODE 0: out0 = acc0 + acc1;  MODE 1: out0 = acc0 - 3 acc1 (value plane carried raw codes), out1 = acc1.
 // OUT  0: int64 store, 1: int64 atomicAdd (split-K), 2: finalized float64 (fz_col = colscale[K] | colshift[K] in smem).
-enum { kOutStore = 0, kOutAtomic = 1, kOutFused = 2 };
+//      3: as 2, plus the column statistics of the finalized output (FusedFinalize::stats_partial).
+enum { kOutStore = 0, kOutAtomic = 1, kOutFused = 2, kOutFusedStats = 3 };
+// Statistics accumulators (kOutFusedStats): every epilogue thread (= output row of a tile) keeps its own running
+// max / max / sum per column in shared memory, [column slot][3][kEpilogueWarps * 32] doubles, folded once per kernel.
+constexpr int kStatThreads = kEpilogueWarps * 32;
 // Pair modes.  The operand image is the dominant L2 -> SM traffic (every m-tile re-reads all of it); processing two
 // m-tiles against one staged chunk halves it.  M: missing data, issuer i runs plane i of both tiles (4 accumulators of
 // 64 columns); E: no missing data, issuer i takes K-blocks of parity i of both tiles (4 x 64); T: no missing data and
@@ -177,7 +188,7 @@ __device__ __forceinline__ long long planes_to_int64(const uint32_t* r) {
 template <int P, int MODE, int OUT>
 __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t tbase, uint32_t acc_full,
                                               uint32_t acc_empty, int warp, int lane, int acc_sets, uint32_t acc_w,
-                                              const double* fz_col) {
+                                              const double* fz_col, double* stats_acc) {
   const int q = warp & 3;  // TMEM lane quarter this warp may touch
   const int row = q * 32 + lane;
   const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
@@ -188,6 +199,11 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
   const int n_work = p.m_units * p.splits;
   const int shift1 = p.has_missing ? kMissShift : kValueShift;
   const int tiles_per_item = p.pair ? 2 : 1;
+  // running column statistics (kOutFusedStats): this thread's own accumulators, no atomics, fixed order
+  double* my_stats = stats_acc + (warp - kEpilogueWarp0) * 32 + lane;
+  if (OUT == kOutFusedStats) {
+    for (int i = 0; i < p.stats_cols * 3; ++i) my_stats[i * kStatThreads] = 0.0;
+  }
   uint32_t tile_no = 0;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
     const int unit = w % p.m_units;
@@ -207,7 +223,7 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
       double row_a = 0.0, row_scale = 1.0, row_shift = 1.0;
       double* fdst = nullptr;
       float* fdst32 = nullptr;
-      if (OUT == kOutFused && live) {
+      if (OUT >= kOutFused && live) {
         if (p.fz.rowa) row_a = __ldg(p.fz.rowa + m);
         if (p.fz.rowscale) row_scale = __ldg(p.fz.rowscale + m);
         if (p.fz.rowshift) row_shift = __ldg(p.fz.rowshift + m);
@@ -248,13 +264,35 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
           const int a0 = (int)r0[i] >> kValueShift;
           const int a1 = (int)r1[i] >> shift1;
           if (MODE == 1) {
-            r0[i] = (uint32_t)(OUT == kOutFused ? a0 : a0 - 3 * a1);
+            r0[i] = (uint32_t)(OUT >= kOutFused ? a0 : a0 - 3 * a1);
             r1[i] = (uint32_t)a1;
           } else {
             r0[i] = (uint32_t)(a0 + a1);
           }
         }
         const int k_hi = min(8, K - g * 8);
+        if (OUT == kOutFusedStats) {
+          // what colstats_partial_kernel computes for the next A.dot: max |y| d, max |y| d mu, sum w y
+          const double abs_scale = fabs(row_scale), abs_a = fabs(row_a);
+          double* acc = my_stats + (size_t)(((g - g_first) / kSplit) * 8 * 3) * kStatThreads;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            if (kk < k_hi) {
+              const int k = g * 8 + kk;
+              double v = (double)planes_to_int64<P>(r0 + kk * P) * row_scale;
+              if (MODE == 1) v = fma((double)planes_to_int64<P>(r1 + kk * P), row_a3, v);
+              const double y = fma(v, fz_col[k], row_shift * fz_col[128 + k]);
+              fdst[k] = y;
+              double* a = acc + kk * 3 * kStatThreads;
+              double v1 = fabs(y) * abs_scale;
+              if (v1 != v1) v1 = INFINITY;   // NaN poisons the scale, as in the stand-alone pass
+              const double v2 = v1 * abs_a;
+              if (v1 > a[0]) a[0] = v1;
+              if (v2 > a[kStatThreads]) a[kStatThreads] = v2;
+              a[2 * kStatThreads] = fma(row_shift, y, a[2 * kStatThreads]);
+            }
+          }
+        } else {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           if (kk < k_hi) {
@@ -288,23 +326,46 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
             }
           }
         }
+        }
       }
     }
+  }
+  if (OUT == kOutFusedStats) {
+    // fold the rows in a fixed order: one partial row per CTA, the layout colstats_finish_kernel reads
+    asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
+    const int k = (warp - kEpilogueWarp0) * 32 + lane;
+    if (k < K) {
+      const int g = k >> 3;
+      const double* base = stats_acc + (size_t)(((g / kSplit) * 8 + (k & 7)) * 3) * kStatThreads + (g % kSplit) * 128;
+      double m1 = 0.0, m2 = 0.0, ws = 0.0;
+      for (int r = 0; r < 128; ++r) {
+        m1 = fmax(m1, base[r]);
+        m2 = fmax(m2, base[kStatThreads + r]);
+        ws += base[2 * kStatThreads + r];
+      }
+      double* out = p.fz.stats_partial + (size_t)blockIdx.x * 3 * K;
+      out[k] = m1;
+      out[K + k] = m2;
+      out[2 * K + k] = ws;
+    }
+    if (blockIdx.x == 0 && k == 0) *p.fz.stats_nblocks = (double)gridDim.x;
   }
 }
 
 template <int P>
 __device__ __forceinline__ void epilogue_dispatch(const GenoMmaParams& p, uint32_t tbase, uint32_t acc_full,
                                                   uint32_t acc_empty, int warp, int lane, int acc_sets, uint32_t acc_w,
-                                                  const double* fz_col) {
+                                                  const double* fz_col, double* stats_acc) {
 #define LMDEC_EPI(MODE, OUT) \
-  epilogue_loop<P, MODE, OUT>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col)
+  epilogue_loop<P, MODE, OUT>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col, stats_acc)
   if (p.mode == 1) {
-    if (p.fuse) LMDEC_EPI(1, kOutFused);
+    if (p.fuse == 2) LMDEC_EPI(1, kOutFusedStats);
+    else if (p.fuse) LMDEC_EPI(1, kOutFused);
     else if (p.use_atomics) LMDEC_EPI(1, kOutAtomic);
     else LMDEC_EPI(1, kOutStore);
   } else {
-    if (p.fuse) LMDEC_EPI(0, kOutFused);
+    if (p.fuse == 2) LMDEC_EPI(0, kOutFusedStats);
+    else if (p.fuse) LMDEC_EPI(0, kOutFused);
     else if (p.use_atomics) LMDEC_EPI(0, kOutAtomic);
     else LMDEC_EPI(0, kOutStore);
   }
@@ -570,12 +631,13 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 11..14)
+    // ------------------------------------------------------------------ epilogue
+    double* stats_acc = reinterpret_cast<double*>(smem + p.stats_off);
     switch (p.P) {
-      case 1: epilogue_dispatch<1>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col); break;
-      case 2: epilogue_dispatch<2>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col); break;
-      case 3: epilogue_dispatch<3>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col); break;
-      default: epilogue_dispatch<4>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col); break;
+      case 1: epilogue_dispatch<1>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col, stats_acc); break;
+      case 2: epilogue_dispatch<2>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col, stats_acc); break;
+      case 3: epilogue_dispatch<3>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col, stats_acc); break;
+      default: epilogue_dispatch<4>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col, stats_acc); break;
     }
   }
   tc_fence_before_sync();

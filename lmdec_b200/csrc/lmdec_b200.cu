@@ -325,8 +325,10 @@ __global__ void __launch_bounds__(256) colstats_partial_kernel(const TB* __restr
                                                                int64_t kd_limit, int K, const double* __restrict__ row1,
                                                                const double* __restrict__ row2,
                                                                const double* __restrict__ w, int use_w,
-                                                               double* __restrict__ partial) {
+                                                               double* __restrict__ partial,
+                                                               double* __restrict__ n_blocks_out) {
   extern __shared__ double sm[];
+  if (n_blocks_out && blockIdx.x == 0 && threadIdx.x == 0) *n_blocks_out = (double)gridDim.x;
   const int k = threadIdx.x % K, ry = threadIdx.x / K, rpb = blockDim.x / K;
   double m1 = 0.0, m2 = 0.0, ws = 0.0;
   if (ry < rpb) {
@@ -374,10 +376,13 @@ __global__ void __launch_bounds__(256) colstats_partial_kernel(const TB* __restr
 }
 // stats layout: [0,K) mult, [K,2K) 1/mult, [2K,3K) shift = shift_sign * wsum, [3K,4K) amax, [4K,5K) amax2
 // 1024 threads: thread (slice, k) folds blocks slice, slice+S, ... ; thread k then folds the slices in order.
+// n_blocks < 0: the count is read from n_blocks_dev (partials emitted by an earlier launch).
 __global__ void __launch_bounds__(1024) colstats_finish_kernel(const double* __restrict__ partial, int n_blocks, int K,
                                                                double lim, double shift_sign,
-                                                               double* __restrict__ stats) {
+                                                               double* __restrict__ stats,
+                                                               const double* __restrict__ n_blocks_dev) {
   extern __shared__ double sm[];
+  if (n_blocks < 0) n_blocks = (int)*n_blocks_dev;
   const int n_sl = blockDim.x / K;
   const int k = threadIdx.x % K, sl = threadIdx.x / K;
   double m1 = 0.0, m2 = 0.0, ws = 0.0;
@@ -959,7 +964,7 @@ int lmdec_colabsmax(const double* B, int64_t ldb, int64_t kd_limit, int K, const
 static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
                            int has_missing, int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N,
                            int64_t* out0, int64_t* out1, int splits, void* stream, const FusedFinalize* fz,
-                           bool* fused) {
+                           bool* fused, bool* stats_emitted = nullptr) {
   if (N % 16 || N < 16 || N > 128 || K * P > N || P < 1 || P > 4) return fail("lmdec_geno_matmul: bad K/P/N");
   if (m_limit <= 0 || m_limit > M || kd_limit <= 0 || kd_limit > Kd) return fail("lmdec_geno_matmul: bad limits");
   if (mode == 1 && (!has_missing || !out1)) return fail("lmdec_geno_matmul: mode 1 needs has_missing and out1");
@@ -1040,11 +1045,33 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
   if (fz && !p.use_atomics) {
     p.fz = *fz;
     p.fuse = 1;
+    if (fz->stats_partial) {
+      if (K <= 32 && !fz->out_f32 && fz->stats_nblocks) p.fuse = 2;   // epilogue also emits the output's column statistics
+      else p.fz.stats_partial = nullptr;
+    }
     if (fused) *fused = true;
   }
+  if (stats_emitted) *stats_emitted = p.fuse == 2;
   const size_t stage_bytes = (size_t)8 * N * 32 * p.n_img;
-  const size_t scratch = 0;
   const size_t budget = 222 * 1024;  // 227 KB per CTA minus the static barriers / column constants (3 KB) and slack
+  // statistics accumulators of the epilogue threads (fuse == 2): [column slot][3][256] doubles behind the rings
+  size_t scratch = 0;
+  if (p.fuse == 2) {
+    const int split = kEpilogueWarps / 4;
+    int cols = 0;
+    for (int g = 0; g * 8 < K; ++g) {
+      const int hi = (g / split) * 8 + (K - 8 * g < 8 ? K - 8 * g : 8);
+      if (hi > cols) cols = hi;
+    }
+    p.stats_cols = cols;
+    scratch = (size_t)cols * 3 * kEpilogueWarps * 32 * sizeof(double);
+    if (scratch + (size_t)kMaxTileStages * kTileBytes + 2 * stage_bytes > budget) {   // no room: stand-alone pass
+      scratch = 0;
+      p.fuse = 1;
+      p.fz.stats_partial = nullptr;
+      if (stats_emitted) *stats_emitted = false;
+    }
+  }
   int tile_stages = kMaxTileStages, b_stages = 0;
   for (; tile_stages >= 2; tile_stages /= 2) {
     b_stages = (int)((budget - scratch - (size_t)tile_stages * kTileBytes) / stage_bytes);
@@ -1052,6 +1079,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
   }
   if (b_stages > kMaxBStages) b_stages = kMaxBStages;
   if (b_stages < 2 || tile_stages < 2) return fail("lmdec_geno_matmul: shared memory budget");
+  p.stats_off = (int)((size_t)tile_stages * kTileBytes + b_stages * stage_bytes);
   p.b_stages = b_stages;
   p.tile_stages = tile_stages;
   const size_t smem = (size_t)tile_stages * kTileBytes + b_stages * stage_bytes + scratch;
@@ -1146,7 +1174,26 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
   return check_launch("lmdec_sqdiff", 2);
 }
 
-int64_t lmdec_apply_work_doubles(int K) { return (int64_t)5 * K + (int64_t)kStatsMaxBlocks * 3 * K; }
+int64_t lmdec_apply_work_doubles(int K) { return (int64_t)5 * K + 1 + (int64_t)kStatsMaxBlocks * 3 * K; }
+
+// column statistics of a float64 / float32 operand -> partial rows (+ their count in *n_blocks_out when given)
+static int launch_colstats_partial(const void* B, bool b_f32, int64_t ldb, int64_t kd_limit, int K, const double* row1,
+                                   const double* row2, const double* w, int use_w, double* partial,
+                                   double* n_blocks_out, cudaStream_t st, int* blocks_out) {
+  const int rpb = 256 / K > 0 ? 256 / K : 1;
+  int64_t blocks = cdiv(kd_limit, (int64_t)rpb * 8);
+  if (blocks > kStatsMaxBlocks) blocks = kStatsMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  const int threads = 256;
+  if (b_f32)
+    colstats_partial_kernel<float><<<(unsigned)blocks, threads, 3 * threads * sizeof(double), st>>>(
+        (const float*)B, ldb, kd_limit, K, row1, row2, w, use_w, partial, n_blocks_out);
+  else
+    colstats_partial_kernel<double><<<(unsigned)blocks, threads, 3 * threads * sizeof(double), st>>>(
+        (const double*)B, ldb, kd_limit, K, row1, row2, w, use_w, partial, n_blocks_out);
+  if (blocks_out) *blocks_out = (int)blocks;
+  return 0;
+}
 
 int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
                          int has_missing, int transpose_flags, const void* B, int64_t ldb, int K, int P,
@@ -1158,44 +1205,40 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
   const bool reuse_operand = (transpose_flags & 2) != 0;  // stats + plane images of B are already in work / image1/2
   const bool b_f32 = (transpose_flags & 4) != 0;          // B is float32 (else float64)
   const bool out_f32 = (transpose_flags & 8) != 0;        // out is float32 (else float64)
+  const bool emit_stats = (transpose_flags & 16) != 0;    // A^T y only: leave out's column statistics in work
+  const bool stats_ready = (transpose_flags & 32) != 0;   // A t only: B's column statistics are already in work
   const int N = (K * P + 15) / 16 * 16;
   if (N > 128) return fail("lmdec_operator_apply: K*P needs more than 128 tensor-core columns");
   if (has_missing && !impute) return fail("lmdec_operator_apply: has_missing needs the imputation vector");
   if (has_missing && ((!transpose && !image2) || (transpose && !acc1)))
     return fail("lmdec_operator_apply: has_missing needs image2 (A.dot) / acc1 (A.T.dot)");
+  if ((emit_stats && !transpose) || (stats_ready && (transpose || reuse_operand)))
+    return fail("lmdec_operator_apply: flag 16 goes with A.T.dot, flag 32 with A.dot");
   cudaStream_t st = (cudaStream_t)stream;
   double* stats = work;
-  double* partial = work + 5 * K;
+  double* n_blocks_dev = work + 5 * K;
+  double* partial = work + 5 * K + 1;
   const bool two = has_missing && !transpose;
   // ---- column statistics -> fixed-point multiplier and rank-1 shift
-  const int rpb = 256 / K > 0 ? 256 / K : 1;
-  int64_t blocks = cdiv(kd_limit, (int64_t)rpb * 8);
-  if (blocks > kStatsMaxBlocks) blocks = kStatsMaxBlocks;
-  if (blocks < 1) blocks = 1;
-  const int threads = 256;
   const double lim = ldexp(1.0, 8 * P - (two ? 3 : 2));
   int rc = 0;
   if (!reuse_operand) {
-  if (b_f32)
-    colstats_partial_kernel<float><<<(unsigned)blocks, threads, 3 * threads * sizeof(double), st>>>(
-        (const float*)B, ldb, kd_limit, K, transpose ? nullptr : scale, two ? impute : nullptr,
-        transpose ? nullptr : center_w, center_w != nullptr, partial);
-  else
-    colstats_partial_kernel<double><<<(unsigned)blocks, threads, 3 * threads * sizeof(double), st>>>(
-        (const double*)B, ldb, kd_limit, K, transpose ? nullptr : scale, two ? impute : nullptr,
-        transpose ? nullptr : center_w, center_w != nullptr, partial);
-  colstats_finish_kernel<<<1, 1024, (size_t)(1024 / K) * 3 * K * sizeof(double), st>>>(partial, (int)blocks, K, lim,
-                                                                                          -1.0, stats);
-  rc = check_launch("lmdec_operator_apply (colstats)", 2);
-  if (rc) return rc;
-  // ---- int8 planes
-  rc = b_f32 ? quantize_planes_t<float>((const float*)B, ldb, Kd, kd_limit, K, P, N, stats,
-                                        transpose ? nullptr : scale, two ? impute : nullptr, image1,
-                                        two ? image2 : nullptr, stream)
-             : quantize_planes_t<double>((const double*)B, ldb, Kd, kd_limit, K, P, N, stats,
-                                         transpose ? nullptr : scale, two ? impute : nullptr, image1,
-                                         two ? image2 : nullptr, stream);
-  if (rc) return rc;
+    int blocks = -1;
+    if (!stats_ready)
+      launch_colstats_partial(B, b_f32, ldb, kd_limit, K, transpose ? nullptr : scale, two ? impute : nullptr,
+                              transpose ? nullptr : center_w, center_w != nullptr, partial, nullptr, st, &blocks);
+    colstats_finish_kernel<<<1, 1024, (size_t)(1024 / K) * 3 * K * sizeof(double), st>>>(partial, blocks, K, lim, -1.0,
+                                                                                            stats, n_blocks_dev);
+    rc = check_launch("lmdec_operator_apply (colstats)", stats_ready ? 1 : 2);
+    if (rc) return rc;
+    // ---- int8 planes
+    rc = b_f32 ? quantize_planes_t<float>((const float*)B, ldb, Kd, kd_limit, K, P, N, stats,
+                                          transpose ? nullptr : scale, two ? impute : nullptr, image1,
+                                          two ? image2 : nullptr, stream)
+               : quantize_planes_t<double>((const double*)B, ldb, Kd, kd_limit, K, P, N, stats,
+                                           transpose ? nullptr : scale, two ? impute : nullptr, image1,
+                                           two ? image2 : nullptr, stream);
+    if (rc) return rc;
   }
   // ---- tensor-core product, with the diagonal / rank-1 terms fused into its epilogue when it is not split
   FusedFinalize fz;
@@ -1207,18 +1250,32 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
   fz.out = out;
   fz.ldo = ldo;
   fz.out_f32 = out_f32 ? 1 : 0;
-  bool fused = false;
+  fz.stats_partial = emit_stats ? partial : nullptr;
+  fz.stats_nblocks = emit_stats ? n_blocks_dev : nullptr;
+  bool fused = false, emitted = false;
   rc = launch_geno_mma(store, M, Kd, m_limit, kd_limit, has_missing, (transpose && has_missing) ? 1 : 0, image1,
                        two ? image2 : nullptr, K, P, N, acc0, (transpose && has_missing) ? acc1 : nullptr, 0, stream,
-                       &fz, &fused);
-  if (rc || fused) return rc;
-  if (!out_f32)
-    return lmdec_finalize(acc0, fz.rowa ? acc1 : nullptr, m_limit, K, fz.colscale, fz.rowa, fz.rowscale, fz.rowshift,
+                       &fz, &fused, &emitted);
+  if (rc) return rc;
+  if (!fused) {
+    if (!out_f32)
+      rc = lmdec_finalize(acc0, fz.rowa ? acc1 : nullptr, m_limit, K, fz.colscale, fz.rowa, fz.rowscale, fz.rowshift,
                           fz.colshift, (double*)out, ldo, stream);
-  finalize_kernel<float><<<(unsigned)cdiv(m_limit * K, 256), 256, 0, st>>>(
-      (const long long*)acc0, (const long long*)(fz.rowa ? acc1 : nullptr), m_limit, K, fz.colscale, fz.rowa,
-      fz.rowscale, fz.rowshift, fz.colshift, (float*)out, ldo);
-  return check_launch("lmdec_operator_apply (finalize)");
+    else {
+      finalize_kernel<float><<<(unsigned)cdiv(m_limit * K, 256), 256, 0, st>>>(
+          (const long long*)acc0, (const long long*)(fz.rowa ? acc1 : nullptr), m_limit, K, fz.colscale, fz.rowa,
+          fz.rowscale, fz.rowshift, fz.colshift, (float*)out, ldo);
+      rc = check_launch("lmdec_operator_apply (finalize)");
+    }
+    if (rc) return rc;
+  }
+  if (emit_stats && !emitted) {
+    // the epilogue could not take the statistics along (split contraction, K > 32 or float32 out): one pass over out
+    launch_colstats_partial(out, out_f32, ldo, m_limit, K, scale, has_missing ? impute : nullptr, center_w,
+                            center_w != nullptr, partial, n_blocks_dev, st, nullptr);
+    rc = check_launch("lmdec_operator_apply (output colstats)");
+  }
+  return rc;
 }
 
 int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, double* r, int* flag, void* stream) {

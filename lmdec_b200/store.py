@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Optional
 
 import numpy as np
@@ -29,6 +30,8 @@ from .device import F64, DeviceArray, as_tensor, require_cuda
 
 _DTYPE_CODE = {torch.int8: 0, torch.uint8: 1, torch.float32: 2, torch.float64: 3}
 
+
+_FUSED_STATS = os.environ.get("LMDEC_FUSED_STATS", "1") != "0"   # A/B switch: statistics of t = A^T q from the epilogue
 
 # bench.py sets this to a list to time the dominant kernel with CUDA events on the launching stream
 KERNEL_EVENTS = None
@@ -325,9 +328,11 @@ class GenotypeOperator:
 
     # ------------------------------------------------------------------ the two products (torch tensors in/out)
     def _apply(self, b_in: torch.Tensor, transpose: bool, out: torch.Tensor = None, m_range=None,
-               reuse_operand: bool = False, out_dtype=F64) -> torch.Tensor:
+               reuse_operand: bool = False, out_dtype=F64, emit_stats: bool = False) -> torch.Tensor:
         """One lmdec_operator_apply call; `m_range` = (m0, m1) restricts the OUTPUT rows (m0 a multiple of 128).
-        b_in may be float64 or float32; the result is `out_dtype` (float64 or float32)."""
+        b_in may be float64 or float32; the result is `out_dtype` (float64 or float32).  `emit_stats` (A^T y): the
+        product also leaves the column statistics of its result in the work buffer; an A.dot of exactly that tensor
+        (same object, not modified since) then skips the statistics pass over its p x K operand."""
         st, lib = self.store, self.store.lib
         K = b_in.shape[1]
         buf = self._buffers(K)
@@ -340,8 +345,15 @@ class GenotypeOperator:
             out = torch.empty((m_lim, K), dtype=out_dtype, device=st.device)
         flags = int(transpose) | (2 if reuse_operand else 0) | (4 if b_in.dtype == torch.float32 else 0) | \
             (8 if out.dtype == torch.float32 else 0)
+        emitted = None if reuse_operand else buf.pop("emitted", None)   # any other product reuses the work buffer
         if m == 0:
             return out.zero_() if transpose else out
+        if not transpose and emitted is not None and not reuse_operand and m_range is None:
+            ref, version = emitted
+            if ref() is b_in and b_in._version == version:
+                flags |= 32
+        if transpose and emit_stats and m_range is None and _FUSED_STATS:
+            flags |= 16
         m0, m1 = (0, m_lim) if m_range is None else m_range
         if m0 % 128 or not (0 <= m0 < m1 <= m_lim):
             raise ValueError("bad output row range")
@@ -363,6 +375,8 @@ class GenotypeOperator:
                 _capi.ptr(buf["acc0"]), _capi.ptr(buf["acc1"]), off(out, K * out.element_size()), K,
                 _capi.stream_ptr()),
                 "lmdec_operator_apply")
+        if flags & 16:
+            buf["emitted"] = (weakref.ref(out), out._version)
         return out
 
     def dot_t(self, t: torch.Tensor) -> torch.Tensor:
@@ -404,7 +418,7 @@ class GenotypeOperator:
         if y.stride(1) != 1 or y.stride(0) != y.shape[1]:
             y = y.contiguous()
         if self.store.group is None:
-            w = self._apply(y, True, out_dtype=out_dtype)
+            w = self._apply(y, True, out_dtype=out_dtype, emit_stats=True)
         else:
             w = self._tdot_sharded(y, out_dtype)
         return w[:, 0] if squeeze else w

@@ -343,3 +343,36 @@ def test_dense_float32_tf32x3_matches_float64(cuda):
     u, s, v = np.linalg.svd(a.astype(np.float64), full_matrices=False)
     U, S, V = PowerMethod(k=3, buffer=10, tol=1e-10, factor=None, lmbd=0, max_iter=300).svd(ChainedArray([a]), verbose=False)
     np.testing.assert_allclose(_np(S), s[:3], rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,p,K,miss", [(300, 2000, 20, 0.05), (130, 700, 5, 0.0), (257, 1500, 32, 0.1)])
+def test_epilogue_column_statistics_match_standalone_pass(cuda, n, p, K, miss):
+    """A^T y leaves the statistics of its result for the following A t (lmdec_operator_apply flags 16 / 32): same
+    fixed-point multiplier bit for bit, same rank-1 shift to rounding, and the same product."""
+    import torch
+    from lmdec_b200.decomp import make_snp_array
+    rng = np.random.default_rng(n + p)
+    g = rng.binomial(2, rng.uniform(0.05, 0.5, size=p), size=(n, p)).astype(float)
+    if miss:
+        g[rng.random((n, p)) < miss] = np.nan
+    op = make_snp_array(g, std_method="binom")
+    y = torch.from_numpy(rng.standard_normal((n, K))).to(cuda)
+    t = op.tdot_t(y)
+    buf = op._buffers(K)
+    assert "emitted" in buf
+    x_fused = op.dot_t(t)
+    stats_fused = buf["work"][:5 * K].cpu().numpy().copy()
+    assert "emitted" not in buf
+    x_plain = op.dot_t(t.clone())                      # another tensor object: the stand-alone statistics pass runs
+    stats_plain = buf["work"][:5 * K].cpu().numpy().copy()
+    assert np.array_equal(stats_fused[:2 * K], stats_plain[:2 * K])           # mult, 1/mult
+    assert np.array_equal(stats_fused[3 * K:], stats_plain[3 * K:])           # amax, amax2
+    bound = 2.0 * stats_plain[3 * K:4 * K].max() * p          # sum_r |w_r t_rk| <= p max|mu| max|d t|
+    np.testing.assert_allclose(stats_fused[2 * K:3 * K], stats_plain[2 * K:3 * K], rtol=0, atol=1e-14 * bound)
+    np.testing.assert_allclose(x_fused.cpu().numpy(), x_plain.cpu().numpy(), rtol=0,
+                               atol=1e-9 * np.abs(x_plain.cpu().numpy()).max())
+    t2 = op.tdot_t(y)
+    t2 += 1.0                                           # modified in place: the emitted statistics no longer apply
+    x_mod = op.dot_t(t2)
+    x_ref = op.dot_t(t2.clone())
+    assert np.array_equal(x_mod.cpu().numpy(), x_ref.cpu().numpy())
