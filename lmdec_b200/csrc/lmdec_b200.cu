@@ -222,6 +222,54 @@ __global__ void store_transpose_kernel(const uint8_t* __restrict__ src, int64_t 
 // writes the P plane units of image 1 (and of image 2).  Unit (kb, h, n) sits at ((kb*2 + h)*N + n)*16 bytes; byte e of
 // a unit is MMA contraction index 16h + e, which the producers' decode maps to genotype position
 // 16h + (e>>2) + 4*(e&3) of the K-block (geno_mma.cuh decode16).  Column n = k*P + plane.
+// Fixed point: q = round(x mult) (|q| < 2^(8P-2) by the choice of mult), balanced base-256 digits d_i in [-128, 127].
+// All P digits of q at once: the bytes of q + sum_i 128*256^i are d_i + 128, so (q + bias) ^ bias holds digit i in
+// byte i.  Four rows' digit words are then transposed into one 32-bit word per plane with byte permutes.
+template <int P>
+__device__ __forceinline__ uint32_t digit_bytes(int q) {
+  constexpr uint32_t kBias = P == 1 ? 0x80u : P == 2 ? 0x8080u : P == 3 ? 0x808080u : 0x80808080u;
+  return ((uint32_t)q + kBias) ^ kBias;
+}
+template <int P>
+__device__ __forceinline__ void planes_of_four(const uint32_t* t, uint32_t (&w)[4]) {
+  const uint32_t a = __byte_perm(t[0], t[1], 0x5140), b = __byte_perm(t[2], t[3], 0x5140);
+  w[0] = __byte_perm(a, b, 0x5410);
+  if (P > 1) w[1] = __byte_perm(a, b, 0x7632);
+  if (P > 2) {
+    const uint32_t c = __byte_perm(t[0], t[1], 0x7362), d = __byte_perm(t[2], t[3], 0x7362);
+    w[2] = __byte_perm(c, d, 0x5410);
+    if (P > 3) w[3] = __byte_perm(c, d, 0x7632);
+  }
+}
+
+template <int P, typename TB, bool kFull>
+__device__ __forceinline__ void quantize_rows(const TB* __restrict__ bp, int64_t ldb, int64_t g0, int64_t kd_limit,
+                                              double mk, const double* __restrict__ row1,
+                                              const double* __restrict__ row2, bool two, uint32_t (&t1)[16],
+                                              uint32_t (&t2)[16]) {
+  // q = round(x) for |x| < 2^31 is the low word of x + 1.5*2^52 (one DADD, round-to-nearest-even like rint)
+  constexpr double kMagic = 6755399441055744.0;
+  // largest magnitude P balanced base-256 digits can hold: 127 * (256^P - 1) / 255
+  constexpr int kQmax = P == 1 ? 127 : P == 2 ? 32639 : P == 3 ? 8355711 : 2139062143;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int r = (e >> 2) + 4 * (e & 3);
+    if (kFull || g0 + r < kd_limit) {
+      double x = (double)bp[r * ldb] * mk;
+      if (row1) x *= row1[g0 + r];
+      const int q1 = __double2loint(x + kMagic);
+      t1[e] = digit_bytes<P>(q1);
+      if (two) {
+        // the product kernel multiplies RAW codes (3 at a missing entry) by image 1: image 2 carries q2 - 3 q1
+        const int q2 = __double2loint(x * row2[g0 + r] + kMagic) - 3 * q1;
+        t2[e] = digit_bytes<P>(min(max(q2, -kQmax), kQmax));
+      }
+    }
+  }
+}
+
+// grid: block b takes groups [b*gpb, (b+1)*gpb), thread (tg, k) = threadIdx.x / kq, % kq; kq = N / P columns per group
+// (k < K real, K <= k < kq zero padding); the thread of the last column also zeroes columns [kq*P, N).
 template <int P, typename TB>
 __global__ void __launch_bounds__(256) quantize_planes_kernel(const TB* __restrict__ B, int64_t ldb,
                                                               int64_t kd_limit, int K, int N,
@@ -229,74 +277,42 @@ __global__ void __launch_bounds__(256) quantize_planes_kernel(const TB* __restri
                                                               const double* __restrict__ row1,
                                                               const double* __restrict__ row2,
                                                               int8_t* __restrict__ image1, int8_t* __restrict__ image2,
-                                                              int64_t n_groups) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int kq = N / P;                       // columns handled per group: k < K real, K <= k < kq zero padding
-  if (idx >= n_groups * kq) return;
-  const int k = (int)(idx % kq);
-  const int64_t grp = idx / kq;               // grp = kb*2 + h
-  // q = round(x) for |x| < 2^31 is the low word of x + 1.5*2^52 (one DADD, round-to-nearest-even like rint)
-  constexpr double kMagic = 6755399441055744.0;
-  int q1[16], q2[16];
+                                                              int64_t n_groups, int kq, int gpb) {
+  const int tg = (int)threadIdx.x / kq;
+  const int k = (int)threadIdx.x - tg * kq;
+  const int64_t grp = (int64_t)blockIdx.x * gpb + tg;   // grp = kb*2 + h
+  if (tg >= gpb || grp >= n_groups) return;
+  uint32_t t1[16], t2[16];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) q1[e] = q2[e] = 0;
+  for (int e = 0; e < 16; ++e) t1[e] = t2[e] = 0;
+  const bool two = image2 != nullptr;
   if (k < K) {
     const double mk = mult[k];
-    // largest magnitude P balanced base-256 digits can hold: 127 * (256^P - 1) / 255
-    const int qmax = (int)(127.0 * (ldexp(1.0, 8 * P) - 1.0) / 255.0);
     const int64_t g0 = grp * 16;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const int64_t g = g0 + (e >> 2) + 4 * (e & 3);
-      if (g < kd_limit) {
-        double x = (double)B[g * ldb + k] * mk;
-        if (row1) x *= row1[g];
-        x = fmin(fmax(x, (double)-qmax), (double)qmax);
-        q1[e] = __double2loint(x + kMagic);
-        if (image2) {
-          // the product kernel multiplies RAW codes (3 at a missing entry) by image 1: image 2 carries q2 - 3 q1
-          const double x2 = fmin(fmax(x * row2[g], (double)-qmax), (double)qmax);
-          q2[e] = min(max(__double2loint(x2 + kMagic) - 3 * q1[e], -qmax), qmax);
-        }
-      }
-    }
+    const TB* bp = B + g0 * ldb + k;
+    if (g0 + 16 <= kd_limit) quantize_rows<P, TB, true>(bp, ldb, g0, kd_limit, mk, row1, row2, two, t1, t2);
+    else if (g0 < kd_limit) quantize_rows<P, TB, false>(bp, ldb, g0, kd_limit, mk, row1, row2, two, t1, t2);
   }
-  // balanced base-256 digits: the stored byte of plane pl is the low byte of q_pl, q_{pl+1} = (q_pl + 128) >> 8
   const size_t base = ((size_t)grp * N + (size_t)k * P) * 16;
+  uint32_t w1[4][4], w2[4][4];   // [row quad][plane]
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    planes_of_four<P>(t1 + 4 * j, w1[j]);
+    if (two) planes_of_four<P>(t2 + 4 * j, w2[j]);
+  }
 #pragma unroll
   for (int pl = 0; pl < P; ++pl) {
-    uint32_t w1[4], w2[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t lo = __byte_perm((uint32_t)q1[4 * j], (uint32_t)q1[4 * j + 1], 0x0040);
-      const uint32_t hi = __byte_perm((uint32_t)q1[4 * j + 2], (uint32_t)q1[4 * j + 3], 0x0040);
-      w1[j] = __byte_perm(lo, hi, 0x5410);
-      if (image2) {
-        const uint32_t lo2 = __byte_perm((uint32_t)q2[4 * j], (uint32_t)q2[4 * j + 1], 0x0040);
-        const uint32_t hi2 = __byte_perm((uint32_t)q2[4 * j + 2], (uint32_t)q2[4 * j + 3], 0x0040);
-        w2[j] = __byte_perm(lo2, hi2, 0x5410);
-      }
-    }
-    *reinterpret_cast<uint4*>(image1 + base + pl * 16) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-    if (image2) *reinterpret_cast<uint4*>(image2 + base + pl * 16) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-    if (pl + 1 < P) {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        q1[e] = (q1[e] + 128) >> 8;
-        q2[e] = (q2[e] + 128) >> 8;
-      }
+    *reinterpret_cast<uint4*>(image1 + base + pl * 16) = make_uint4(w1[0][pl], w1[1][pl], w1[2][pl], w1[3][pl]);
+    if (two) *reinterpret_cast<uint4*>(image2 + base + pl * 16) = make_uint4(w2[0][pl], w2[1][pl], w2[2][pl], w2[3][pl]);
+  }
+  if (k == kq - 1) {
+    // columns [kq*P, N) are not covered by the groups when P does not divide N: zero them
+    for (int n = kq * P; n < N; ++n) {
+      const size_t off = ((size_t)grp * N + n) * 16;
+      *reinterpret_cast<uint4*>(image1 + off) = make_uint4(0, 0, 0, 0);
+      if (two) *reinterpret_cast<uint4*>(image2 + off) = make_uint4(0, 0, 0, 0);
     }
   }
-}
-// columns [ (N/P)*P, N ) are not covered by the groups above when P does not divide N: zero them
-__global__ void quantize_tail_kernel(int8_t* __restrict__ image1, int8_t* __restrict__ image2, int N, int n0,
-                                     int64_t n_groups) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int w = N - n0;
-  if (idx >= n_groups * w) return;
-  const size_t off = ((size_t)(idx / w) * N + n0 + (idx % w)) * 16;
-  *reinterpret_cast<uint4*>(image1 + off) = make_uint4(0, 0, 0, 0);
-  if (image2) *reinterpret_cast<uint4*>(image2 + off) = make_uint4(0, 0, 0, 0);
 }
 
 __global__ void colabsmax_kernel(const double* __restrict__ B, int64_t ldb, int64_t kd_limit, int K,
@@ -917,10 +933,12 @@ static int quantize_planes_t(const TB* B, int64_t ldb, int64_t Kd, int64_t kd_li
   if (kd_limit > Kd) return fail("lmdec_quantize_planes: kd_limit > Kd");
   const int64_t n_groups = cdiv(Kd, 256) * 8 * 2;
   const int kq = N / P;
-  const unsigned blocks = (unsigned)cdiv(n_groups * kq, 256);
+  const int gpb = 256 / kq;          // groups per block (kq <= 128)
+  const unsigned blocks = (unsigned)cdiv(n_groups, gpb);
   cudaStream_t st_ = (cudaStream_t)stream;
-#define LMDEC_Q(PP) \
-  quantize_planes_kernel<PP, TB><<<blocks, 256, 0, st_>>>(B, ldb, kd_limit, K, N, mult, row1, row2, image1, image2, n_groups)
+#define LMDEC_Q(PP)                                                                                              \
+  quantize_planes_kernel<PP, TB><<<blocks, 256, 0, st_>>>(B, ldb, kd_limit, K, N, mult, row1, row2, image1, image2, \
+                                                          n_groups, kq, gpb)
   switch (P) {
     case 1: LMDEC_Q(1); break;
     case 2: LMDEC_Q(2); break;
@@ -928,9 +946,6 @@ static int quantize_planes_t(const TB* B, int64_t ldb, int64_t Kd, int64_t kd_li
     default: LMDEC_Q(4); break;
   }
 #undef LMDEC_Q
-  if (kq * P < N)
-    quantize_tail_kernel<<<(unsigned)cdiv(n_groups * (N - kq * P), 256), 256, 0, st_>>>(image1, image2, N, kq * P,
-                                                                                        n_groups);
   return check_launch("lmdec_quantize_planes");
 }
 
