@@ -176,6 +176,9 @@ int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const in
 void lmdec_set_sm_reserve(int n_sms);
 /* 1 (default): long contractions process two 128-row tiles per staged operand chunk; 0: one tile (A/B comparison). */
 void lmdec_set_pair_mode(int on);
+/* Tuning / A-B switch: 2 (default) = two MMA issuer pairs take alternate contraction chunks of single-tile work items,
+ * 1 = one pair issues every chunk.  Results are identical (integer accumulation). */
+void lmdec_set_issuer_groups(int groups);
 
 /* CUDA-event timing of lmdec_geno_matmul's kernel on its launching stream (bench.py's roofline figure). */
 void lmdec_kernel_timing(int on);

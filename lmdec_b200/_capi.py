@@ -41,6 +41,7 @@ SIGNATURES = {
     "lmdec_kernel_timing": (None, [_i32]),
     "lmdec_set_sm_reserve": (None, [_i32]),
     "lmdec_set_pair_mode": (None, [_i32]),
+    "lmdec_set_issuer_groups": (None, [_i32]),
     "lmdec_kernel_timing_read": (_i32, [_p, _p]),
     "lmdec_sqdiff": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p]),
 }
@@ -69,6 +70,8 @@ def load():
         fn.argtypes = args
     if os.environ.get("LMDEC_PAIR_MODE") is not None:      # A/B switch for the two-tiles-per-operand-chunk schedule
         lib.lmdec_set_pair_mode(int(os.environ["LMDEC_PAIR_MODE"]))
+    if os.environ.get("LMDEC_ISSUER_GROUPS"):
+        lib.lmdec_set_issuer_groups(int(os.environ["LMDEC_ISSUER_GROUPS"]))
     _LIB = lib
     return lib
 

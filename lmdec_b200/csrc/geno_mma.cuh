@@ -57,7 +57,7 @@ constexpr uint32_t kTileBytes = 8192;
 // mbarrier slots (8 bytes each) in one shared array, addressed by 32-bit shared-window addresses
 constexpr int kMaxAStages = 8;
 constexpr int kBarFullT = 0, kBarEmptyT = 8, kBarFullA = 16, kBarEmptyA = 24, kBarFullB = 32, kBarEmptyB = 36,
-              kBarAccFull = 40, kBarAccEmpty = 42, kNumBars = 44;
+              kBarAccFull = 40, kBarAccEmpty = 42, kBarFirstDone = 44, kNumBars = 48;
 
 // out[m,k] = (acc0 + rowa[m]*acc1) * colscale[k] * rowscale[m] + rowshift[m] * colshift[k]   (NULL = absent / 1)
 struct FusedFinalize {
@@ -79,7 +79,7 @@ struct FusedFinalize {
 #ifdef LMDEC_TRACE
 // debug timeline: CTA 0 records clock64() stamps of its first kTraceChunks chunks (tools/trace_mma.py prints them)
 constexpr int kTraceChunks = 64;
-__device__ long long g_trace[8][kTraceChunks];
+__device__ long long g_trace[12][kTraceChunks];
 #define LMDEC_STAMP(row, idx) do { if (blockIdx.x == 0 && (idx) < kTraceChunks) g_trace[row][idx] = clock64(); } while (0)
 #else
 #define LMDEC_STAMP(row, idx) do { } while (0)
@@ -110,6 +110,7 @@ struct GenoMmaParams {
   int m_units;             // work items per split: m_tiles, or ceil(m_tiles / 2) in pair mode
   int stats_off;           // byte offset of the statistics accumulators in dynamic shared memory (fuse == 2)
   int stats_cols;          // column slots per epilogue thread
+  int issuer_groups;       // 2: chunk-interleaved issuer pairs (single-tile work items)
   int fuse;                // write the finalized float64 result from the epilogue (never with atomics)
   FusedFinalize fz;
 };
@@ -372,6 +373,119 @@ __device__ __forceinline__ void epilogue_dispatch(const GenoMmaParams& p, uint32
 #undef LMDEC_EPI
 }
 
+// MMA issuer warp.  The whole warp runs the loop (uniform control flow keeps the operand arithmetic on the uniform
+// datapath); one elected lane issues.  With a plain `if (lane == 0)` ptxas wraps every UTCIMMA operand in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~100 cycles per MMA, profiles/r01).
+//   kPair: schedule (kPairNone / M / E / T);  kMiss: value + indicator planes (else K-block parity per issuer);
+//   kIlv: single tiles, issuer pair `issuer >> 1` takes the chunks of that parity within a work item.
+template <int kPair, bool kMiss, bool kIlv>
+__device__ __forceinline__ void issuer_loop(const GenoMmaParams& p, int issuer, int lane, uint32_t tbase, uint32_t bar0,
+                                            uint32_t smem_b_a, int n_work, int chunks_per_split) {
+  constexpr bool quad = kIssuerWarps == 4 && kPair == kPairM;
+  constexpr int tiles_per_item = kPair ? 2 : 1;
+  constexpr bool all_kb = kMiss || kPair == kPairT;   // this issuer runs all 8 K-blocks of a chunk (else parity me)
+  const uint32_t empty_a = bar0 + 8 * kBarEmptyA, full_a = bar0 + 8 * kBarFullA;
+  const uint32_t full_b = bar0 + 8 * kBarFullB, empty_b = bar0 + 8 * kBarEmptyB;
+  const uint32_t acc_full = bar0 + 8 * kBarAccFull, acc_empty = bar0 + 8 * kBarAccEmpty;
+  const uint32_t first_done = bar0 + 8 * kBarFirstDone;
+  const int N = p.N;
+  const uint32_t img_bytes = (uint32_t)kKbPerChunk * N * 32;
+  const uint32_t stage_bytes = img_bytes * p.n_img;
+  const uint32_t a_stage_cols = kMiss ? 128 : 64;
+  const uint32_t acc_w = N <= 64 ? 64 : 128;
+  const int acc_sets = p.acc_sets;
+  const uint32_t a_stages = (uint32_t)p.a_stages, b_stages = (uint32_t)p.b_stages;
+  const int me = issuer & 1;            // plane (missing data) or K-block parity
+  const int hi = issuer >> 1;           // quad: the tile of the pair this issuer owns; kIlv: its chunk parity
+  const uint32_t idesc = make_idesc_i8(128, (uint32_t)N, 0, 1);
+  const uint32_t lbo = (uint32_t)N * 16;
+  const uint32_t plane = kMiss ? (uint32_t)me : 0u;
+  const uint32_t img = (kMiss && p.n_img == 2) ? (uint32_t)me : 0u;
+  // descriptor of the B ring base; stage / image / K-block offsets are added to its 16-byte address field
+  const uint64_t bdesc_ring = make_smem_desc(smem_b_a, lbo, 128) + (uint64_t)((img * img_bytes) >> 4);
+  const uint32_t a_ring = tbase + (uint32_t)p.a_ring_col0 + plane * 64;
+  const uint32_t kb_step = (uint32_t)(2 * N);  // one K-block of the image, in 16-byte units
+  uint32_t a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
+  uint32_t tile_no = 0;
+  int tr = 0;
+  (void)tr;
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
+    const int sp = w / p.m_units;
+    const int c0 = sp * chunks_per_split;
+    const int c1 = min(c0 + chunks_per_split, p.n_chunks);
+    const uint32_t set = kPair ? 0u : tile_no % acc_sets;
+    const uint32_t set_phase = kPair ? (tile_no & 1) : ((tile_no / acc_sets) & 1);
+    mbar_wait_a(acc_empty + 8 * set, set_phase ^ 1);
+    tc_fence_after_sync();
+    uint32_t accumulate[2] = {0, 0};
+    // interleaved pairs: pair 0 owns the first chunk of the work item and its first MMA overwrites the accumulator;
+    // pair 1 may only add to it after that MMA has completed (first_done, one barrier per accumulator)
+    bool ordered = !kIlv || hi == 0;
+    if (kIlv && hi == 1) accumulate[0] = 1;
+    for (int c = c0; c < c1; ++c) {
+      const bool my_chunk = !kIlv || ((c - c0) & 1) == hi;
+      uint64_t bdesc0 = 0;
+      if (my_chunk) {
+        mbar_wait_a(full_b + 8 * b_stage, b_phase);
+        if (issuer == 0 && lane == 0) LMDEC_STAMP(6, tr);   // B stage full seen by issuer 0
+        bdesc0 = bdesc_ring + (uint64_t)((b_stage * stage_bytes) >> 4);
+      }
+#pragma unroll
+      for (int t = 0; t < tiles_per_item; ++t) {
+        const bool mine = my_chunk && (quad ? (t == hi) : (kPair != kPairT || t == me));
+        if (mine) {
+          mbar_wait_a(full_a + 8 * a_stage, a_phase);
+          if (issuer == 0 && lane == 0) LMDEC_STAMP(4, tr);   // A stage full seen by issuer 0
+          tc_fence_after_sync();
+          const uint32_t slot = kPair ? (uint32_t)t : set;
+          const uint32_t d_addr = tbase + (kPair == kPairT ? slot : slot * 2 + me) * acc_w;
+          const uint32_t a_addr = a_ring + a_stage * a_stage_cols;
+          if (kIlv && !ordered) {
+            mbar_wait_a(first_done + 8 * (set * 2 + me), set_phase);
+            tc_fence_after_sync();
+            ordered = true;
+          }
+          if (elect_one()) {
+            if (all_kb) {
+              umma_ts_i8(d_addr, a_addr, bdesc0, idesc, accumulate[t]);
+              if (kIlv && !accumulate[t]) umma_commit_a(first_done + 8 * (set * 2 + me));
+#pragma unroll
+              for (int j = 1; j < kKbPerChunk; ++j)
+                umma_ts_i8(d_addr, a_addr + j * 8, bdesc0 + j * kb_step, idesc, 1u);
+            } else {
+              umma_ts_i8(d_addr, a_addr + me * 8, bdesc0 + me * kb_step, idesc, accumulate[t]);
+              if (kIlv && !accumulate[t]) umma_commit_a(first_done + 8 * (set * 2 + me));
+#pragma unroll
+              for (int j = 1; j < kKbPerChunk / 2; ++j)
+                umma_ts_i8(d_addr, a_addr + (2 * j + me) * 8, bdesc0 + (2 * j + me) * kb_step, idesc, 1u);
+            }
+            umma_commit_a(empty_a + 8 * a_stage);
+          }
+          __syncwarp();
+          if (issuer == 0 && lane == 0) LMDEC_STAMP(5, tr);   // MMAs issued + committed
+          if (issuer == 0) ++tr;
+          accumulate[t] = 1;
+        }
+        if (++a_stage == a_stages) {
+          a_stage = 0;
+          a_phase ^= 1;
+        }
+      }
+      if (my_chunk) {
+        if (elect_one()) umma_commit_a(empty_b + 8 * b_stage);  // after every MMA that reads this B stage
+        __syncwarp();
+        if (issuer == 0 && lane == 0) LMDEC_STAMP(8, tr - 1);   // B stage released
+      }
+      if (++b_stage == b_stages) {
+        b_stage = 0;
+        b_phase ^= 1;
+      }
+    }
+    if (elect_one()) umma_commit_a(acc_full + 8 * set);
+    __syncwarp();
+  }
+}
+
 template <int kGroups>
 __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaParams p) {
   constexpr int kGroupWarps = kProducerWarps / kGroups;   // producer warps per tile-chunk
@@ -385,6 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   const uint32_t full_a = bar0 + 8 * kBarFullA, empty_a = bar0 + 8 * kBarEmptyA;   // decoded A (TMEM ring)
   const uint32_t full_b = bar0 + 8 * kBarFullB, empty_b = bar0 + 8 * kBarEmptyB;   // B image (smem ring)
   const uint32_t acc_full = bar0 + 8 * kBarAccFull, acc_empty = bar0 + 8 * kBarAccEmpty;  // accumulator sets
+  // (kBarFirstDone: [set][accumulator], its overwriting MMA has completed -- interleaved issuer pairs)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N;
@@ -397,7 +512,10 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   // pair mode M with 4 issuer warps: one issuer per (tile, plane) accumulator, so each thread issues 8 instead of 16
   // MMAs per staged operand chunk (a single thread sustains one narrow MMA per ~54 cycles)
   const bool quad = kIssuerWarps == 4 && p.pair == kPairM;
-  const int n_issuers = quad ? 4 : 2;
+  // single tiles: two issuer pairs take alternate chunks, so the per-chunk barrier round trips of an issuing thread
+  // (~900 cycles of waits and commits around ~400 of MMA issue, profiles/r01/pipeline_trace.txt) overlap
+  const bool interleave = kIssuerWarps == 4 && !p.pair && p.issuer_groups == 2;
+  const int n_issuers = (quad || interleave) ? 4 : 2;
   const uint32_t kARingCol0 = (uint32_t)p.a_ring_col0;
   const uint32_t a_stage_cols = p.has_missing ? 128 : 64;
   const int acc_sets = p.acc_sets;
@@ -420,12 +538,13 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     }
     for (int i = 0; i < kMaxBStages; ++i) {
       mbar_init(&bars[kBarFullB + i], 1);
-      mbar_init(&bars[kBarEmptyB + i], n_issuers);
+      mbar_init(&bars[kBarEmptyB + i], quad ? 4 : 2);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[kBarAccFull + i], n_issuers);
       mbar_init(&bars[kBarAccEmpty + i], kEpilogueWarps);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[kBarFirstDone + i], 1);
     mbar_fence_init();
   }
   tc_fence_before_sync();
@@ -551,84 +670,18 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     }
   } else if (warp >= kIssuerWarp0 && warp < kIssuerWarp0 + kIssuerWarps) {
     // ------------------------------------------------------------------ MMA issuers
-    // The whole warp runs the loop (uniform control flow keeps the operand arithmetic on the uniform datapath); one
-    // elected lane issues.  With a plain `if (lane == 0)` ptxas wraps every UTCIMMA operand in an
-    // ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~100 cycles per MMA, profiles/r01).
     if (warp - kIssuerWarp0 < n_issuers) {
       const int issuer = warp - kIssuerWarp0;
-      const int me = issuer & 1;            // plane (missing data) or K-block parity
-      const int my_tile = issuer >> 1;      // quad mode: the tile of the pair this issuer owns
-      const uint32_t idesc = make_idesc_i8(128, (uint32_t)N, 0, 1);
-      const uint32_t lbo = (uint32_t)N * 16;
-      const uint32_t plane = p.has_missing ? (uint32_t)me : 0u;
-      const uint32_t img = (p.has_missing && p.n_img == 2) ? (uint32_t)me : 0u;
-      // descriptor of the B ring base; stage / image / K-block offsets are added to its 16-byte address field
-      const uint64_t bdesc_ring = make_smem_desc(smem_b_a, lbo, 128) + (uint64_t)((img * img_bytes) >> 4);
-      const uint32_t a_ring = tbase + kARingCol0 + plane * 64;
-      const uint32_t kb_step = (uint32_t)(2 * N);  // one K-block of the image, in 16-byte units
-      uint32_t a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
-      uint32_t tile_no = 0;
-      int tr = 0;
-      (void)tr;
-      const bool all_kb = p.has_missing || p.pair == kPairT;  // this issuer runs all 8 K-blocks of a chunk (else parity me)
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
-        const int sp = w / p.m_units;
-        const int c0 = sp * chunks_per_split;
-        const int c1 = min(c0 + chunks_per_split, p.n_chunks);
-        const uint32_t set = p.pair ? 0u : tile_no % acc_sets;
-        const uint32_t set_phase = p.pair ? (tile_no & 1) : ((tile_no / acc_sets) & 1);
-        mbar_wait_a(acc_empty + 8 * set, set_phase ^ 1);
-        tc_fence_after_sync();
-        uint32_t accumulate[2] = {0, 0};
-        for (int c = c0; c < c1; ++c) {
-          mbar_wait_a(full_b + 8 * b_stage, b_phase);
-          const uint64_t bdesc0 = bdesc_ring + (uint64_t)((b_stage * stage_bytes) >> 4);
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (t < tiles_per_item) {
-              const bool mine = quad ? (t == my_tile) : (p.pair != kPairT || t == me);
-              if (mine) {
-                mbar_wait_a(full_a + 8 * a_stage, a_phase);
-                if (issuer == 0 && lane == 0) LMDEC_STAMP(4, tr);   // A stage full seen by issuer 0
-                tc_fence_after_sync();
-                const uint32_t slot = p.pair ? (uint32_t)t : set;
-                const uint32_t d_addr = tbase + (p.pair == kPairT ? slot : slot * 2 + me) * acc_w;
-                const uint32_t a_addr = a_ring + a_stage * a_stage_cols;
-                if (elect_one()) {
-                  if (all_kb) {
-                    umma_ts_i8(d_addr, a_addr, bdesc0, idesc, accumulate[t]);
-#pragma unroll
-                    for (int j = 1; j < kKbPerChunk; ++j)
-                      umma_ts_i8(d_addr, a_addr + j * 8, bdesc0 + j * kb_step, idesc, 1u);
-                  } else {
-                    umma_ts_i8(d_addr, a_addr + me * 8, bdesc0 + me * kb_step, idesc, accumulate[t]);
-#pragma unroll
-                    for (int j = 1; j < kKbPerChunk / 2; ++j)
-                      umma_ts_i8(d_addr, a_addr + (2 * j + me) * 8, bdesc0 + (2 * j + me) * kb_step, idesc, 1u);
-                  }
-                  umma_commit_a(empty_a + 8 * a_stage);
-                }
-                __syncwarp();
-                if (issuer == 0 && lane == 0) LMDEC_STAMP(5, tr);   // MMAs issued + committed
-                if (issuer == 0) ++tr;
-                accumulate[t] = 1;
-              }
-              if (++a_stage == (uint32_t)a_stages) {
-                a_stage = 0;
-                a_phase ^= 1;
-              }
-            }
-          }
-          if (elect_one()) umma_commit_a(empty_b + 8 * b_stage);  // after every MMA that reads this B stage
-          __syncwarp();
-          if (++b_stage == (uint32_t)p.b_stages) {
-            b_stage = 0;
-            b_phase ^= 1;
-          }
-        }
-        if (elect_one()) umma_commit_a(acc_full + 8 * set);
-        __syncwarp();
-      }
+#define LMDEC_ISSUE(PAIR, MISS, ILV) \
+  issuer_loop<PAIR, MISS, ILV>(p, issuer, lane, tbase, bar0, smem_b_a, n_work, chunks_per_split)
+      // one instance per schedule: the issuing thread is the serial bottleneck of the pipeline, every mode test left in
+      // its per-chunk path costs throughput
+      if (p.pair == kPairM) LMDEC_ISSUE(kPairM, true, false);
+      else if (p.pair == kPairE) LMDEC_ISSUE(kPairE, false, false);
+      else if (p.pair == kPairT) LMDEC_ISSUE(kPairT, false, false);
+      else if (p.has_missing) { if (interleave) LMDEC_ISSUE(kPairNone, true, true); else LMDEC_ISSUE(kPairNone, true, false); }
+      else { if (interleave) LMDEC_ISSUE(kPairNone, false, true); else LMDEC_ISSUE(kPairNone, false, false); }
+#undef LMDEC_ISSUE
     }
   } else {
     // ------------------------------------------------------------------ epilogue

@@ -34,6 +34,7 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_mma_events;
 static bool g_mma_timing = false;
 static int g_sm_reserve = 0;
 static int g_pair_min_chunks = 64;
+static int g_issuer_groups = 2;   // single-tile work items: issuer pairs taking alternate chunks (1 = one pair)
 static int g_prod_groups2 = 1;
 static int g_pair_mode = 1;   // lmdec_set_pair_mode: 0 disables the two-tiles-per-B-stage schedule (A/B tests)  // SMs left free for concurrently running collectives (row-sharded runs)
 
@@ -755,21 +756,26 @@ __global__ void __cluster_dims__(kCqrCluster, 1, 1) __launch_bounds__(kCqrThread
   __shared__ double red[kCqrThreads / 32];
   const int64_t row0 = (int64_t)rank * per;
   const int rows = (int)max((int64_t)0, min((int64_t)per, n - row0));
+  if (t == 0) LMDEC_STAMP(7, 0);
   for (int i = t; i < rows * K; i += kCqrThreads) {
     const int r = i / K, c = i - r * K;
     buf0[i] = X[(row0 + r) * ldx + c];
   }
   __syncthreads();
+  if (t == 0) LMDEC_STAMP(7, 1);
   for (int pass = 0; pass < 2; ++pass) {
     double* part = pass ? part2 : part1;
     cqr_gram_local(pass ? buf1 : buf0, rows, K, pacc, part);
+    if (t == 0) LMDEC_STAMP(7, 2 + 8 * pass);
     cluster.sync();
+    if (t == 0) LMDEC_STAMP(7, 3 + 8 * pass);
     for (int i = t; i < kk; i += kCqrThreads) {
       double acc = 0.0;
       for (int c = 0; c < kCqrCluster; ++c) acc += cluster.map_shared_rank(part, c)[i];
       G[i] = acc;
     }
     __syncthreads();
+    if (t == 0) LMDEC_STAMP(7, 4 + 8 * pass);
     if (pass == 1) {   // deviation of the second Gram matrix from the identity (health check of the first pass)
       double dev = 0.0;
       for (int i = t; i < kk; i += kCqrThreads) {
@@ -781,9 +787,11 @@ __global__ void __cluster_dims__(kCqrCluster, 1, 1) __launch_bounds__(kCqrThread
     }
     const int f = block_chol(G, K, rank_tol, Lsm, Lf, vec, ri, pass ? r2 : r1);
     if (t == 0) flags[pass] = f;
+    if (t == 0) LMDEC_STAMP(7, 5 + 8 * pass);
     if (pass == 0) cqr_apply(buf0, rows, K, ri, buf1, K);
     else cqr_apply(buf1, rows, K, ri, Q + row0 * ldq, ldq);
     __syncthreads();
+    if (t == 0) LMDEC_STAMP(7, 6 + 8 * pass);
   }
   if (rank == 0) {
     for (int i = t; i < kk; i += kCqrThreads) {
@@ -801,6 +809,7 @@ __global__ void __cluster_dims__(kCqrCluster, 1, 1) __launch_bounds__(kCqrThread
     }
   }
   cluster.sync();   // peers may still be reading this CTA's part2
+  if (t == 0) LMDEC_STAMP(7, 16);
 }
 
 __global__ void qvals_kernel(const double* __restrict__ si, const double* __restrict__ sj, int k, int scale,
@@ -1017,6 +1026,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
     else if (!has_missing) p.pair = kPairT;
   }
   p.m_units = p.pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  p.issuer_groups = g_issuer_groups;
   // TMEM budget (512 columns): accumulators first, the rest is the decoded-A ring.  Short contractions alternate two
   // accumulator sets so the epilogue overlaps the next tile; long ones (epilogue negligible) give the columns to a
   // deeper A ring instead.
@@ -1392,7 +1402,7 @@ int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const in
 // ---- CUDA-event timing of the dominant kernel (bench.py's roofline): events are recorded on the launching stream
 #ifdef LMDEC_TRACE
 int lmdec_trace_read(long long* host_out) {
-  return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 8 * kTraceChunks);
+  return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 12 * kTraceChunks);
 }
 #endif
 
@@ -1400,6 +1410,8 @@ void lmdec_set_pair_mode(int on) {
   g_pair_mode = on != 0;
   if (on > 1) g_pair_min_chunks = on;  // values > 1 also set the shortest contraction (in 256-wide chunks) that pairs
 }
+
+void lmdec_set_issuer_groups(int groups) { g_issuer_groups = groups == 1 ? 1 : 2; }
 
 void lmdec_set_sm_reserve(int n_sms) { g_sm_reserve = n_sms < 0 ? 0 : n_sms; }
 

@@ -20,19 +20,21 @@ y = torch.randn((n, K), dtype=torch.float64, device=dev)
 for _ in range(3):
     (op.dot_t(t) if which == "dot" else op.tdot_t(y))
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * (8 * 64))()
+buf = (ctypes.c_longlong * (12 * 64))()
 lib.lmdec_trace_read.argtypes = [ctypes.c_void_p]
 lib.lmdec_trace_read(buf)
-tr = np.frombuffer(buf, dtype=np.int64).reshape(8, 64).copy()
+tr = np.frombuffer(buf, dtype=np.int64).reshape(12, 64).copy()
 t0 = tr[0, 0]
-names = ["tile arrived", "A stage free", "decode issued", "st complete", "issuer sees full", "mma committed"]
+names = ["tile arrived", "A stage free", "decode issued", "st complete", "issuer sees full", "mma committed", "B full seen"]
 print(f"{which} missing={miss}: cycles relative to the first event; one row per (tile-)chunk")
 print("chunk " + " ".join(f"{nm:>17s}" for nm in names) + "   period")
 for c in range(8, 40):
-    row = [tr[r, c] - t0 for r in range(6)]
+    row = [tr[r, c] - t0 for r in range(7)]
     print(f"{c:5d} " + " ".join(f"{v:17d}" for v in row) + f"   {tr[3, c] - tr[3, c - 1]:6d}")
 d = np.diff(tr[3, 8:56])
 print("median period (cycles per tile-chunk):", np.median(d))
 print("median decode (A free -> decode issued):", np.median(tr[2, 8:56] - tr[1, 8:56]), " st wait:", np.median(tr[3, 8:56] - tr[2, 8:56]))
 print("median producer wait for A stage (tile arrived -> A free):", np.median(tr[1, 8:56] - tr[0, 8:56]))
 print("median issuer: full seen -> committed:", np.median(tr[5, 8:56] - tr[4, 8:56]), "; st complete -> issuer sees full:", np.median(tr[4, 8:56] - tr[3, 8:56]))
+print("median issuer: previous commit -> B full seen:", np.median(tr[6, 9:56] - tr[5, 8:55]), "; B full seen -> A full seen:", np.median(tr[4, 8:56] - tr[6, 8:56]))
+print("median issuer: commit -> B released:", np.median(tr[8, 8:55] - tr[5, 8:55]), "; B released -> next B full seen:", np.median(tr[6, 9:56] - tr[8, 8:55]))
