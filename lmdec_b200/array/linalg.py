@@ -129,12 +129,17 @@ class _PendingQR:
         return host[:K * K].reshape(K, K)
 
 
-def orthonormalize_begin(x: torch.Tensor, group=None) -> _PendingQR:
+def orthonormalize_begin(x: torch.Tensor, group=None, stats_for=None) -> _PendingQR:
     """Enqueue CholeskyQR2 entirely on the device (both K x K factorizations included) and return without syncing, so
-    the caller can queue the next products behind it before asking for r."""
+    the caller can queue the next products behind it before asking for r.  `stats_for`: the operator whose A^T product
+    consumes q next; when it offers `qr_stats_slot`, the single-launch kernel leaves q's column statistics there."""
     K = x.shape[1]
     if group is None and x.dtype == F64 and _SMALL_QR and cholqr2_small_fits(x.shape[0], K):
-        q, packed = cholqr2_small(x)                   # one launch for the whole CholeskyQR2
+        slot = getattr(stats_for, "qr_stats_slot", None)
+        work = slot(x.shape[0], K) if slot is not None else None
+        q, packed = cholqr2_small(x, stats_work=work)  # one launch for the whole CholeskyQR2
+        if work is not None:
+            stats_for.qr_stats_emitted(q)
         return _PendingQR(q, packed, K)
     if group is None:
         _, ri1, r1, f1 = gram_chol(x)                  # 2 launches per pass, nothing else

@@ -684,46 +684,98 @@ __device__ int block_chol(const double* __restrict__ G, int K, double rank_tol, 
   return __syncthreads_or(bad);
 }
 
-// Gram matrix of this CTA's row slice (shared memory) -> part[K*K]; upper triangle computed once, mirrored.
+// float64 tensor-core step D[8x8] += A[8x4] B[4x8]: lane holds A[lane>>2][lane&3], B[lane&3][lane>>2] and
+// D[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int kCqrWarps = kCqrThreads / 32;
+constexpr int kCqrPaccDoubles = kCqrWarps * 64;   // one 8x8 partial tile per warp
+
+// Gram matrix of this CTA's row slice (shared memory, [rows][K]) -> part[K*K].  The 8x8 tiles of the upper triangle go
+// to warps (tile, row split); each warp runs the slice through DMMA (k = 4 rows per step, two accumulator pairs in
+// flight) and the splits are folded in a fixed order.
 __device__ void cqr_gram_local(const double* __restrict__ sl, int rows, int K, double* __restrict__ pacc,
                                double* __restrict__ part) {
-  const int t = threadIdx.x;
-  const int npairs = K * (K + 1) / 2;
-  const int H = kCqrThreads / npairs >= 2 ? 2 : 1;       // row halves when the thread count allows
-  const int per = (rows + H - 1) / H;
-  for (int o = t; o < npairs * H; o += kCqrThreads) {
-    const int h = o / npairs;
-    int e = 0, rem = o - h * npairs;
-    while (rem >= K - e) { rem -= K - e; ++e; }
-    const int f = e + rem;
-    const int lo = h * per, hi = min(rows, lo + per);
-    double a0 = 0.0, a1 = 0.0;
-    int r = lo;
-    for (; r + 1 < hi; r += 2) {
-      a0 += sl[r * K + e] * sl[r * K + f];
-      a1 += sl[(r + 1) * K + e] * sl[(r + 1) * K + f];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int nt = (K + 7) >> 3, ntile = nt * (nt + 1) / 2;
+  const int nsplit = kCqrWarps / ntile;            // >= 1 (nt <= 4 -> ntile <= 10)
+  const int split = warp / ntile;
+  if (split < nsplit) {
+    int ta = 0, rem = warp - split * ntile;
+    while (rem >= nt - ta) { rem -= nt - ta; ++ta; }
+    const int tb = ta + rem;
+    const int per = ((rows + nsplit - 1) / nsplit + 3) & ~3;
+    const int lo = split * per, hi = min(rows, lo + per);
+    const int j = lane & 3, i = lane >> 2;
+    const int ca = ta * 8 + i, cb = tb * 8 + i;
+    const bool oka = ca < K, okb = cb < K;
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    int r = lo + j;
+    for (; r - j + 4 < hi; r += 8) {
+      const double a0 = oka ? sl[r * K + ca] : 0.0, b0 = okb ? sl[r * K + cb] : 0.0;
+      const bool in1 = r + 4 < hi;
+      const double a1 = (oka && in1) ? sl[(r + 4) * K + ca] : 0.0, b1 = (okb && in1) ? sl[(r + 4) * K + cb] : 0.0;
+      dmma884(c0, c1, a0, b0);
+      dmma884(d0, d1, a1, b1);
     }
-    if (r < hi) a0 += sl[r * K + e] * sl[r * K + f];
-    pacc[o] = a0 + a1;
+    if (r - j < hi) {
+      const bool in0 = r < hi;
+      dmma884(c0, c1, (oka && in0) ? sl[r * K + ca] : 0.0, (okb && in0) ? sl[r * K + cb] : 0.0);
+    }
+    double* o = pacc + (size_t)warp * 64 + i * 8 + 2 * j;
+    o[0] = c0 + d0;
+    o[1] = c1 + d1;
   }
   __syncthreads();
-  for (int i = t; i < K * K; i += kCqrThreads) {
-    int a = i / K, b = i - a * K;
+  for (int e = t; e < K * K; e += kCqrThreads) {
+    int a = e / K, b = e - a * K;
     if (a > b) { const int w = a; a = b; b = w; }
-    const int pr = a * K - a * (a - 1) / 2 + (b - a);
-    part[i] = H == 2 ? pacc[pr] + pacc[npairs + pr] : pacc[pr];
+    const int ta = a >> 3, tb = b >> 3;
+    const int idx = ta * nt - ta * (ta - 1) / 2 + (tb - ta);
+    double acc = 0.0;
+    for (int s_ = 0; s_ < nsplit; ++s_) acc += pacc[(size_t)(s_ * ntile + idx) * 64 + (a & 7) * 8 + (b & 7)];
+    part[e] = acc;
   }
 }
 
-// out[r][b] = sum_{a <= b} in[r][a] r_inv[a][b]; one thread per element
+// out[r][b] = sum_{a <= b} in[r][a] r_inv[a][b] by DMMA: warp -> 8-row tiles, k = 4 columns of `in` per step; r_inv is
+// upper triangular, so steps beyond the column tile are skipped.
 __device__ void cqr_apply(const double* __restrict__ in, int rows, int K, const double* __restrict__ r_inv,
                           double* __restrict__ out, int64_t ldo) {
-  for (int i = threadIdx.x; i < rows * K; i += kCqrThreads) {
-    const int r = i / K, b = i - r * K;
-    const double* row = in + r * K;
-    double acc = 0.0;
-    for (int a = 0; a <= b; ++a) acc += row[a] * r_inv[a * K + b];
-    out[(int64_t)r * ldo + b] = acc;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = lane & 3, i = lane >> 2;
+  const int nt = (K + 7) >> 3, mt = (rows + 7) >> 3;
+  for (int tb = 0; tb < nt; ++tb) {
+    const int n0 = tb * 8;
+    const int ks = min((K + 3) >> 2, 2 * tb + 2);       // 4s <= n0 + 7
+    double bf[8];
+#pragma unroll
+    for (int s_ = 0; s_ < 8; ++s_) {
+      const int a = 4 * s_ + j, b = n0 + i;
+      bf[s_] = (s_ < ks && a < K && b < K) ? r_inv[a * K + b] : 0.0;
+    }
+    for (int tm = warp; tm < mt; tm += kCqrWarps) {
+      const int r = tm * 8 + i;
+      const bool okr = r < rows;
+      const double* row = in + r * K;
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int s_ = 0; s_ < 8; ++s_) {
+        if (s_ < ks) {
+          const int a = 4 * s_ + j;
+          dmma884(c0, c1, (okr && a < K) ? row[a] : 0.0, bf[s_]);
+        }
+      }
+      const int b = n0 + 2 * j;
+      if (okr) {
+        if (b < K) out[(int64_t)r * ldo + b] = c0;
+        if (b + 1 < K) out[(int64_t)r * ldo + b + 1] = c1;
+      }
+    }
   }
 }
 
@@ -733,7 +785,8 @@ __device__ void cqr_apply(const double* __restrict__ in, int rows, int K, const 
 // packed = [r2 r1 | flag1 | flag2 | max|Q1^T Q1 - I|] as qr_pack_kernel writes it.
 __global__ void __cluster_dims__(kCqrCluster, 1, 1) __launch_bounds__(kCqrThreads)
     cholqr2_small_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int K, int per, double rank_tol,
-                         double* __restrict__ Q, int64_t ldq, double* __restrict__ packed) {
+                         double* __restrict__ Q, int64_t ldq, double* __restrict__ packed,
+                         double* __restrict__ stats_work) {
   extern __shared__ double cqr_sm[];
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -744,8 +797,8 @@ __global__ void __cluster_dims__(kCqrCluster, 1, 1) __launch_bounds__(kCqrThread
   double* buf1 = buf0 + (size_t)per * K;  // [per][K] first-pass output
   double* part1 = buf1 + (size_t)per * K; // Gram partial of pass 1 (read by the peers)
   double* part2 = part1 + kk;
-  double* pacc = part2 + kk;              // [2][K(K+1)/2] <= kk + K
-  double* G = pacc + kk + K;
+  double* pacc = part2 + kk;              // [warps][8][8] partial Gram tiles
+  double* G = pacc + kCqrPaccDoubles;
   double* Lsm = G + kk;
   double* Lf = Lsm + kk;
   double* vec = Lf + kk;                  // [4][K]
@@ -792,6 +845,37 @@ __global__ void __cluster_dims__(kCqrCluster, 1, 1) __launch_bounds__(kCqrThread
     else cqr_apply(buf1, rows, K, ri, Q + row0 * ldq, ldq);
     __syncthreads();
     if (t == 0) LMDEC_STAMP(7, 6 + 8 * pass);
+  }
+  if (stats_work) {
+    // column statistics of Q as the operand of the A^T q that follows (what colstats_partial_kernel computes for it:
+    // max |q|, -, sum q per column), one partial row per CTA in the operator's work buffer
+    const int n_sl = kCqrThreads / K;
+    const int k = t % K, sl = t / K;
+    if (sl < n_sl) {
+      double m1 = 0.0, ws = 0.0;
+      for (int r = sl; r < rows; r += n_sl) {
+        const double y = Q[(row0 + r) * ldq + k];
+        double v = fabs(y);
+        if (v != v) v = INFINITY;
+        m1 = fmax(m1, v);
+        ws += y;
+      }
+      pacc[sl * K + k] = m1;
+      pacc[kCqrThreads + sl * K + k] = ws;
+    }
+    __syncthreads();
+    if (t < K) {
+      double m1 = 0.0, ws = 0.0;
+      for (int j = 0; j < n_sl; ++j) {
+        m1 = fmax(m1, pacc[j * K + t]);
+        ws += pacc[kCqrThreads + j * K + t];
+      }
+      double* out = stats_work + 5 * K + 1 + (size_t)rank * 3 * K;
+      out[t] = m1;
+      out[K + t] = 0.0;
+      out[2 * K + t] = ws;
+    }
+    if (rank == 0 && t == 0) stats_work[5 * K] = (double)kCqrCluster;
   }
   if (rank == 0) {
     for (int i = t; i < kk; i += kCqrThreads) {
@@ -1237,8 +1321,8 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
   if (has_missing && !impute) return fail("lmdec_operator_apply: has_missing needs the imputation vector");
   if (has_missing && ((!transpose && !image2) || (transpose && !acc1)))
     return fail("lmdec_operator_apply: has_missing needs image2 (A.dot) / acc1 (A.T.dot)");
-  if ((emit_stats && !transpose) || (stats_ready && (transpose || reuse_operand)))
-    return fail("lmdec_operator_apply: flag 16 goes with A.T.dot, flag 32 with A.dot");
+  if ((emit_stats && !transpose) || (stats_ready && reuse_operand))
+    return fail("lmdec_operator_apply: flag 16 goes with A.T.dot, flag 32 excludes flag 2");
   cudaStream_t st = (cudaStream_t)stream;
   double* stats = work;
   double* n_blocks_dev = work + 5 * K;
@@ -1370,19 +1454,19 @@ int lmdec_gram_chol(const double* X, int64_t ldx, int64_t m, int K, double rank_
 int64_t lmdec_cholqr2_small_max_elems(void) { return (int64_t)kCqrCluster * kCqrSliceDoubles; }
 
 int lmdec_cholqr2_small(const double* X, int64_t ldx, int64_t n, int K, double rank_tol, double* Q, int64_t ldq,
-                        double* packed, void* stream) {
+                        double* packed, double* stats_work, void* stream) {
   if (K < 1 || K > 32) return fail("lmdec_cholqr2_small: K out of range (1..32)");
   if (n < 1 || Q == X) return fail("lmdec_cholqr2_small: needs n >= 1 and an output distinct from the input");
   const int64_t per = (n + kCqrCluster - 1) / kCqrCluster;
   if (per * K > kCqrSliceDoubles) return fail("lmdec_cholqr2_small: iterate too large (see lmdec_cholqr2_small_max_elems)");
-  const size_t smem = ((size_t)2 * per * K + 10 * K * K + 5 * K) * sizeof(double);
+  const size_t smem = ((size_t)2 * per * K + 9 * K * K + 4 * K + kCqrPaccDoubles) * sizeof(double);
   static thread_local bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(cholqr2_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     attr_set = true;
   }
   cholqr2_small_kernel<<<kCqrCluster, kCqrThreads, smem, (cudaStream_t)stream>>>(X, ldx, n, K, (int)per, rank_tol, Q,
-                                                                                 ldq, packed);
+                                                                                 ldq, packed, stats_work);
   return check_launch("lmdec_cholqr2_small");
 }
 

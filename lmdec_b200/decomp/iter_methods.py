@@ -187,7 +187,7 @@ class PowerMethod(_IterAlgo):
             group = _group_of(self.array)
             K = x.shape[1]
             if x.is_cuda and K <= 128:
-                pend = orthonormalize_begin(x, group)
+                pend = orthonormalize_begin(x, group, stats_for=self.array)
                 st = self._cache = {"x": x, "q": pend.q}
                 if self.speculate:
                     self._next(st)

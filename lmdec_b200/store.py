@@ -348,9 +348,10 @@ class GenotypeOperator:
         emitted = None if reuse_operand else buf.pop("emitted", None)   # any other product reuses the work buffer
         if m == 0:
             return out.zero_() if transpose else out
-        if not transpose and emitted is not None and not reuse_operand and m_range is None:
-            ref, version = emitted
-            if ref() is b_in and b_in._version == version:
+        if emitted is not None and m_range is None:
+            kind, ref, version = emitted         # statistics of b_in already in the work buffer?
+            if kind == ("q" if transpose else "t") and ref() is b_in and b_in._version == version \
+                    and b_in.shape[0] == kd_lim and b_in.dtype == F64:
                 flags |= 32
         if transpose and emit_stats and m_range is None and _FUSED_STATS:
             flags |= 16
@@ -376,8 +377,20 @@ class GenotypeOperator:
                 _capi.stream_ptr()),
                 "lmdec_operator_apply")
         if flags & 16:
-            buf["emitted"] = (weakref.ref(out), out._version)
+            buf["emitted"] = ("t", weakref.ref(out), out._version)
         return out
+
+    def qr_stats_slot(self, rows: int, K: int):
+        """Work buffer that may receive the column statistics of the iterate q [rows, K] from the orthonormalisation
+        kernel (lmdec_cholqr2_small), or None when the following A^T q cannot use them."""
+        if not _FUSED_STATS or self.store.group is not None or rows != self.rows or _round16(K * self.planes) > 128:
+            return None
+        buf = self._buffers(K)
+        buf.pop("emitted", None)
+        return buf["work"]
+
+    def qr_stats_emitted(self, q: torch.Tensor):
+        self._buffers(q.shape[1])["emitted"] = ("q", weakref.ref(q), q._version)
 
     def dot_t(self, t: torch.Tensor) -> torch.Tensor:
         """x[n_local, K] = A t  for t [p, K] float64 on the device."""

@@ -376,3 +376,31 @@ def test_epilogue_column_statistics_match_standalone_pass(cuda, n, p, K, miss):
     x_mod = op.dot_t(t2)
     x_ref = op.dot_t(t2.clone())
     assert np.array_equal(x_mod.cpu().numpy(), x_ref.cpu().numpy())
+
+
+@pytest.mark.parametrize("n,p,K,miss", [(300, 2000, 20, 0.05), (130, 700, 5, 0.0)])
+def test_qr_kernel_leaves_statistics_for_tdot(cuda, n, p, K, miss):
+    """lmdec_cholqr2_small leaves q's column statistics for the A^T q that follows (flag 32 with transpose)."""
+    import torch
+    from lmdec_b200.array.linalg import orthonormalize_begin
+    from lmdec_b200.decomp import make_snp_array
+    rng = np.random.default_rng(n * 7 + p)
+    g = rng.binomial(2, rng.uniform(0.05, 0.5, size=p), size=(n, p)).astype(float)
+    if miss:
+        g[rng.random((n, p)) < miss] = np.nan
+    op = make_snp_array(g, std_method="binom")
+    x = torch.from_numpy(rng.standard_normal((n, K))).to(cuda)
+    pend = orthonormalize_begin(x, None, stats_for=op)
+    q = pend.q
+    assert pend.finish() is not None
+    buf = op._buffers(K)
+    assert buf["emitted"][0] == "q"
+    t_fused = op.tdot_t(q)
+    stats_fused = buf["work"][:5 * K].cpu().numpy().copy()
+    t_plain = op.tdot_t(q.clone())
+    stats_plain = buf["work"][:5 * K].cpu().numpy().copy()
+    assert np.array_equal(stats_fused[:2 * K], stats_plain[:2 * K])
+    assert np.array_equal(stats_fused[3 * K:4 * K], stats_plain[3 * K:4 * K])
+    np.testing.assert_allclose(stats_fused[2 * K:3 * K], stats_plain[2 * K:3 * K], rtol=0, atol=1e-14 * n)
+    np.testing.assert_allclose(t_fused.cpu().numpy(), t_plain.cpu().numpy(), rtol=0,
+                               atol=1e-9 * np.abs(t_plain.cpu().numpy()).max())
