@@ -138,7 +138,7 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
  * carried in float32 (24-bit mantissa > the 22-bit fixed point it is quantised to), the n x K side in float64.
  * bit 4 (transpose = 1 only) = also leave in `work` the column statistics of `out` taken as the operand of the A.dot
  * that follows in the power iteration (x = A (A^T q), iter_methods.py:383): the tensor-core epilogue reduces them while
- * it writes `out` (K <= 32, float64 out, unsplit contraction; otherwise one extra pass over out);  bit 5 = the column
+ * it writes `out` (K <= 32, unsplit contraction; otherwise one extra pass over out);  bit 5 = the column
  * statistics of B are already in `work` -- left there by the previous A^T product with bit 4 (transpose = 0: B is all
  * m_limit rows of that `out`, unmodified) or by lmdec_cholqr2_small (transpose = 1: B is its Q) -- and the pass over B
  * for them is skipped.

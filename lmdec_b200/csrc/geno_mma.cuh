@@ -69,7 +69,7 @@ struct FusedFinalize {
   void* out;      // float64, or float32 when out_f32
   long long ldo;
   int out_f32;
-  // optional (float64 out, K <= 32): column statistics of the OUTPUT taken as the operand of the following A.dot --
+  // optional (K <= 32): column statistics of the OUTPUT taken as the operand of the following A.dot --
   // per-CTA partials [gridDim.x][3][K] = max|out rowscale|, max|out rowscale rowa|, sum rowshift out (the layout
   // colstats_partial_kernel writes) and the CTA count, so the next product needs no pass over its operand for them
   double* stats_partial;
@@ -282,8 +282,14 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
               const int k = g * 8 + kk;
               double v = (double)planes_to_int64<P>(r0 + kk * P) * row_scale;
               if (MODE == 1) v = fma((double)planes_to_int64<P>(r1 + kk * P), row_a3, v);
-              const double y = fma(v, fz_col[k], row_shift * fz_col[128 + k]);
-              fdst[k] = y;
+              double y = fma(v, fz_col[k], row_shift * fz_col[128 + k]);
+              if (p.fz.out_f32) {
+                const float y32 = (float)y;   // the statistics describe the value the next product will read
+                fdst32[k] = y32;
+                y = (double)y32;
+              } else {
+                fdst[k] = y;
+              }
               double* a = acc + kk * 3 * kStatThreads;
               double v1 = fabs(y) * abs_scale;
               if (v1 != v1) v1 = INFINITY;   // NaN poisons the scale, as in the stand-alone pass

@@ -1155,7 +1155,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
     p.fz = *fz;
     p.fuse = 1;
     if (fz->stats_partial) {
-      if (K <= 32 && !fz->out_f32 && fz->stats_nblocks) p.fuse = 2;   // epilogue also emits the output's column statistics
+      if (K <= 32 && fz->stats_nblocks) p.fuse = 2;   // epilogue also emits the output's column statistics
       else p.fz.stats_partial = nullptr;
     }
     if (fused) *fused = true;
@@ -1379,7 +1379,7 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
     if (rc) return rc;
   }
   if (emit_stats && !emitted) {
-    // the epilogue could not take the statistics along (split contraction, K > 32 or float32 out): one pass over out
+    // the epilogue could not take the statistics along (split contraction or K > 32): one pass over out
     launch_colstats_partial(out, out_f32, ldo, m_limit, K, scale, has_missing ? impute : nullptr, center_w,
                             center_w != nullptr, partial, n_blocks_dev, st, nullptr);
     rc = check_launch("lmdec_operator_apply (output colstats)");

@@ -65,8 +65,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t b
                "r"(bytes)
                : "memory");
 }
+// LMDEC_MBAR_MODE: 0 = try_wait with a long suspend-time hint (park), 1 = try_wait with the default time limit,
+// 2 = test_wait (pure spin)
+#ifndef LMDEC_MBAR_MODE
+#define LMDEC_MBAR_MODE 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if LMDEC_MBAR_MODE == 0
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -74,6 +80,23 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity), "r"(0x00100000u)
       : "memory");
+#elif LMDEC_MBAR_MODE == 1
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {

@@ -351,7 +351,7 @@ class GenotypeOperator:
         if emitted is not None and m_range is None:
             kind, ref, version = emitted         # statistics of b_in already in the work buffer?
             if kind == ("q" if transpose else "t") and ref() is b_in and b_in._version == version \
-                    and b_in.shape[0] == kd_lim and b_in.dtype == F64:
+                    and b_in.shape[0] == kd_lim:
                 flags |= 32
         if transpose and emit_stats and m_range is None and _FUSED_STATS:
             flags |= 16
@@ -409,13 +409,14 @@ class GenotypeOperator:
     @property
     def wide_dtype(self):
         """dtype of the p x K side of the iteration (t = A^T q) on the internal fast path; the public `.T.dot` is
-        always float64.  Row-sharded: float32 -- half the NVLink bytes of the all-reduce, and its 24-bit mantissa is finer
-        than the 22-bit fixed point t is quantised to on its next use (2 x B200: 1.28 vs 1.41 ms per iteration).  Single
-        GPU: float64 (float32 -> float64 conversions in the operand kernels cost more than the halved reads save)."""
+        always float64.  float32: its 24-bit mantissa is finer than the 22-bit fixed point t is quantised to on its next
+        use, the product's epilogue writes half the bytes and the operand kernel of the next product reads half (single
+        GPU 0.752 -> 0.735 ms per iteration), and when row-sharded the all-reduce moves half the NVLink bytes (2 x B200:
+        1.41 -> 1.28 ms).  `LMDEC_WIDE_DTYPE=f64` keeps the wide side in float64."""
         env = os.environ.get("LMDEC_WIDE_DTYPE")
         if env:
             return {"f32": torch.float32, "f64": torch.float64}[env]
-        return torch.float32 if self.store.group is not None else torch.float64
+        return torch.float32
 
     def tdot_t(self, y: torch.Tensor, out_dtype=None) -> torch.Tensor:
         """w[p, K] = A^T y  for y [n_local, K] on the device (all-reduced over ranks when sharded); `out_dtype`
