@@ -30,7 +30,8 @@ def subspace_to_V(x, a, k=None, group=None):
     from .operators import as_operator
     a = as_operator(a)
     x_t = _tdot(a, as_tensor(x)).to(F64)
-    v, _, _ = tsqr_svd(x_t)          # a^T x is replicated on every rank: no collective
+    # sample shards: a^T x is replicated on every rank, no collective; SNP shards: its rows are sharded
+    v, _, _ = tsqr_svd(x_t, getattr(getattr(a, "store", None), "snp_group", None))
     v = v.T
     if k:
         v = v[:k, :]

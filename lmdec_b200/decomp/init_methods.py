@@ -44,7 +44,7 @@ def v_init(array, v, log: int = 0):
 
 def _sub_svd(array, sub_array_t: torch.Tensor, k: int, log: int = 0):
     """SVD of the [p, rows] sample, then v_init with its top-k left vectors (init_methods.py:144-147)."""
-    v, _, _ = tsqr_svd(sub_array_t)
+    v, _, _ = tsqr_svd(sub_array_t, getattr(getattr(array, "store", None), "snp_group", None))
     out = v_init(array, v[:, :k])
     return (out, {}) if log else out
 

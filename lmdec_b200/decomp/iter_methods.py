@@ -50,6 +50,11 @@ def _group_of(op):
     return getattr(getattr(op, "store", None), "group", None) or getattr(op, "group", None)
 
 
+def _snp_group_of(op):
+    """process group over which the SNP (p) axis is sharded, i.e. over which p x K matrices are row-sharded"""
+    return getattr(getattr(op, "store", None), "snp_group", None)
+
+
 def _tdot(op, y):
     return op.tdot_t(y) if hasattr(op, "tdot_t") else op.T.dot_t(y)
 
@@ -294,7 +299,7 @@ class PowerMethod(_IterAlgo):
         if full_v:
             # subspace_to_V (matrix_ops.py:89-99): left singular vectors of A^T x = t r; t is reused by the step
             w = self._t(st).to(F64) @ torch.as_tensor(r, device=dev)
-            v, _, _ = tsqr_svd(w)
+            v, _, _ = tsqr_svd(w, _snp_group_of(self.array))
             V_k = DeviceArray(v.T[:k, :])
         else:
             vh_k = np.ascontiguousarray(vh[:k, :])
@@ -317,7 +322,7 @@ class PowerMethod(_IterAlgo):
             else:  # 'v-subspace'
                 try:
                     prev_V_k = self.history.iter["V"][-1]
-                    acc = subspace_dist(V_k.T, prev_V_k.T, S_np)
+                    acc = subspace_dist(V_k.T, prev_V_k.T, S_np, group=_snp_group_of(self.array))
                 except IndexError:
                     acc = float("INF")
                 self.history.iter["V"].append(V_k)
@@ -325,12 +330,12 @@ class PowerMethod(_IterAlgo):
         return acc_list
 
     def _finalization(self, x, return_history, **kwargs):
-        if self.history.iter["last_value"][2].shape[1] != self.array.shape[1]:
+        if self.history.iter["last_value"][2].shape[1] != getattr(self.array, "local_cols", self.array.shape[1]):
             U, S, _ = self.history.iter["last_value"]
             st = self._cache if self._cache.get("x") is x else None
             if st is not None and "t" in st:
                 w = st["t"].to(F64) @ torch.as_tensor(st["r"], device=x.device)
-                v, _, _ = tsqr_svd(w)
+                v, _, _ = tsqr_svd(w, _snp_group_of(self.array))
                 V = DeviceArray(v.T[:self.k, :])
             else:
                 V = subspace_to_V(x, self.array, self.k)

@@ -87,11 +87,14 @@ def _make_dense_snp_array(array, mean, std, std_method, mask_nan):
 
 def make_snp_array(array, mean: bool = True, std: bool = True, std_method: str = "binom", dtype="int8",
                    rechunk="auto", mask_method: str = "mean", mask_nan: bool = True, planes: int = 3,
-                   device=None, group=None, n_global: Optional[int] = None, row_offset: int = 0) -> GenotypeOperator:
+                   device=None, group=None, n_global: Optional[int] = None, row_offset: int = 0,
+                   snp_group=None, p_global: Optional[int] = None, col_offset: int = 0) -> GenotypeOperator:
     """SNP = ((array + mask) - mean) diag(1/std), lazily, over a device-resident 2-bit store (utils.py:259-289).
 
     `dtype` and `rechunk` are accepted for signature compatibility (the store is always 2-bit, there are no chunks).
     `planes` is the fixed-point width of the tensor-core operand (8*planes - 2 bits below each column's maximum).
+    Multi-GPU (one process per GPU): `array` is this rank's block of samples (`group`, `n_global`, `row_offset`) or of
+    SNPs (`snp_group`, `p_global`, `col_offset`) -- see GenotypeStore.
     """
     if mask_method != "mean":
         raise NotImplementedError(f"mask_method, {mask_method}, is not implemented ")
@@ -100,7 +103,8 @@ def make_snp_array(array, mean: bool = True, std: bool = True, std_method: str =
     else:
         try:
             store = GenotypeStore.from_dense(array, device=device, group=group, n_global=n_global,
-                                             row_offset=row_offset)
+                                             row_offset=row_offset, snp_group=snp_group, p_global=p_global,
+                                             col_offset=col_offset)
         except ValueError:
             # not a genotype matrix (the reference's own tests feed random floats, tests/test_iter_methods.py:12-33):
             # same operator over a dense device matrix, products are library GEMMs

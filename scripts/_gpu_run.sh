@@ -1,2 +1,2 @@
 set -x
-timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -15 > gpurun_out/t1.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench2.log 2>&1

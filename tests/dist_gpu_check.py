@@ -3,8 +3,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tests/dist_gpu_check.py
 
-Every rank holds a block of rows of the same global genotype matrix; the row-sharded PowerMethod / SBPM must reproduce
-the single-GPU result on the full matrix (rank 0 computes it) and the CPU oracle.
+Every rank holds a block of rows (samples) -- then, in a second pass, a block of columns (SNPs) -- of the same global
+genotype matrix; the sharded PowerMethod must reproduce the single-GPU result on the full matrix (rank 0 computes it)
+and the CPU oracle.
 """
 import os
 import sys
@@ -62,6 +63,32 @@ def main():
             print(f"[dist_gpu_check world={world}] {name}: {'ok' if good else 'FAIL'}")
             ok = ok and bool(good)
         print(f"[dist_gpu_check world={world}] iterations {pm.num_iter}, S = {np.round(S, 5)}")
+
+    # ---- SNP shards: every rank holds all samples of a block of SNPs; U, S replicated, V sharded
+    cb = np.linspace(0, p, world + 1).astype(int)
+    c_lo, c_hi = int(cb[rank]), int(cb[rank + 1])
+    for kw2 in (kw, dict(kw, sub_svd_start=True, tol=[1e-7, 1e-9, 1e-9], scoring_method=["q-vals", "v-subspace", "rmse"])):
+        ops = make_snp_array(g[:, c_lo:c_hi], snp_group=dist.group.WORLD, p_global=p, col_offset=c_lo)
+        assert ops.shape == (n, p) and ops.local_cols == c_hi - c_lo
+        pms = PowerMethod(**kw2)
+        args = {} if kw2.get("sub_svd_start") else {"x0": x0}
+        Us, Ss, Vs = pms.svd(ops, verbose=False, **args)
+        v_parts = [None] * world
+        dist.all_gather_object(v_parts, np.asarray(Vs))
+        if rank == 0:
+            V_all = np.concatenate(v_parts, axis=1)
+            Ur, Sr, Vr = oracle.PowerMethod(**kw2).svd(oracle.make_snp_array(g), **args)
+            Us, Ss = np.asarray(Us), np.asarray(Ss)
+            checks = {
+                "SNP shards: V shape": V_all.shape == (k, p),
+                "SNP shards: S vs oracle": np.allclose(Ss, Sr, rtol=1e-4),
+                "SNP shards: U vs oracle": oracle.subspace_dist(Us, Ur, Sr) <= 1e-4,
+                "SNP shards: V vs oracle": oracle.subspace_dist(V_all.T, Vr.T, Sr) <= 1e-4,
+            }
+            for name, good in checks.items():
+                print(f"[dist_gpu_check world={world}] {name} (sub_svd_start={bool(kw2.get('sub_svd_start'))}): "
+                      f"{'ok' if good else 'FAIL'}")
+                ok = ok and bool(good)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
