@@ -118,8 +118,9 @@ def workload_config(n_gpus, shard="snps"):
 # this build
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi in loop mode (one process, a sample every 10 ms) with host timestamps; `summary(t0, t1)` keeps the
-    samples that fall inside the timed region (and reports how many did)."""
+    """SM clock and clock-event (throttle) reasons of one GPU, sampled through NVML from a background thread about
+    every millisecond with host timestamps; `summary(t0, t1)` keeps the samples that fall inside the timed region (and
+    reports how many did).  Falls back to `nvidia-smi -lms 10` when the NVML bindings are missing."""
 
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -128,13 +129,44 @@ class ClockSampler:
     def __init__(self, index):
         self.samples = []   # (host time, sm MHz, max MHz, [active reasons])
         self.proc = None
+        self._stop = False
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self._nvml, self._h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._bits = [(pynvml.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                          (pynvml.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                          (pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                          (pynvml.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-i", str(index), "-lms", "10"], stdout=subprocess.PIPE, text=True)
+            self.source = "nvidia-smi -lms 10"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv, h = self._nvml, self._h
+        while not self._stop:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.samples.append((time.time(), mhz, self._max, [nm for bit, nm in self._bits if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -146,6 +178,7 @@ class ClockSampler:
                 pass
 
     def stop(self):
+        self._stop = True
         if self.proc is not None:
             self.proc.terminate()
 
@@ -156,7 +189,7 @@ class ClockSampler:
         reasons = sorted({r for s in used for r in s[3]})
         return {"sm_mhz": float(np.median([s[1] for s in used])) if used else None,
                 "sm_max_mhz": used[0][2] if used else None, "reasons": reasons, "samples": len(used),
-                "samples_in_timed_region": len(inside), "window": where}
+                "samples_in_timed_region": len(inside), "window": where, "source": self.source}
 
 
 def make_shard(torch, device, n, p, miss, seed):
