@@ -136,9 +136,11 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
  * previous call are reused (several output row ranges of the same product, e.g. to pipeline an all-reduce);
  * bit 2 = B is float32 (else float64); bit 3 = out is float32 (else float64).  The p x K side of the iteration is
  * carried in float32 (24-bit mantissa > the 22-bit fixed point it is quantised to), the n x K side in float64.
- * bit 4 (transpose = 1 only) = also leave in `work` the column statistics of `out` taken as the operand of the A.dot
- * that follows in the power iteration (x = A (A^T q), iter_methods.py:383): the tensor-core epilogue reduces them while
- * it writes `out` (K <= 32, unsplit contraction; otherwise one extra pass over out);  bit 5 = the column
+ * bit 4 (transpose = 1 only) = also leave in `work` the column statistics (fixed-point multiplier, rank-1 shift) of `out`
+ * taken as the operand of the A.dot that follows in the power iteration (x = A (A^T q), iter_methods.py:383): the
+ * tensor-core epilogue reduces them while it writes `out` and the last CTA folds them (K <= 32, unsplit contraction;
+ * otherwise one extra pass over out; uses one device-wide ticket counter, so two such calls must not run concurrently
+ * on different streams);  bit 5 = the column
  * statistics of B are already in `work` -- left there by the previous A^T product with bit 4 (transpose = 0: B is all
  * m_limit rows of that `out`, unmodified) or by lmdec_cholqr2_small (transpose = 1: B is its Q) -- and the pass over B
  * for them is skipped.
@@ -165,11 +167,11 @@ int lmdec_gram_chol(const double* X, int64_t ldx, int64_t m, int K, double rank_
  * 8-CTA cluster (row slices stay in shared memory, Gram partials meet through distributed shared memory; replaces the
  * reference's tsqr of the n x K iterate, lmdec/decomp/iter_methods.py:478-479): Q = orthonormalised X,
  * packed = [r2 r1 (K*K) | flag1 | flag2 | max|Q1^T Q1 - I|].  stats_work (optional): the `work` buffer of the
- * lmdec_operator_apply call that will multiply A^T by Q next; the kernel leaves Q's column statistics there and that call
- * may pass flag 32.  */
+ * lmdec_operator_apply call that will multiply A^T by Q next, stats_lim = 2^(8P-2) for its P planes; the kernel leaves
+ * Q's column statistics there and that call may pass flag 32.  */
 int64_t lmdec_cholqr2_small_max_elems(void);
 int lmdec_cholqr2_small(const double* X, int64_t ldx, int64_t n, int K, double rank_tol, double* Q, int64_t ldq,
-                        double* packed, double* stats_work, void* stream);
+                        double* packed, double* stats_work, double stats_lim, void* stream);
 /* packed[0..K*K) = r2 r1, then flag1, flag2, max|g2 - I|: what the host reads back from one CholeskyQR2. */
 int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const int* flag1, const int* flag2, int K,
                   double* packed, void* stream);

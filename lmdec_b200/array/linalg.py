@@ -136,8 +136,8 @@ def orthonormalize_begin(x: torch.Tensor, group=None, stats_for=None) -> _Pendin
     K = x.shape[1]
     if group is None and x.dtype == F64 and _SMALL_QR and cholqr2_small_fits(x.shape[0], K):
         slot = getattr(stats_for, "qr_stats_slot", None)
-        work = slot(x.shape[0], K) if slot is not None else None
-        q, packed = cholqr2_small(x, stats_work=work)  # one launch for the whole CholeskyQR2
+        work, lim = slot(x.shape[0], K) if slot is not None else (None, 0.0)
+        q, packed = cholqr2_small(x, stats_work=work, stats_lim=lim)  # one launch for the whole CholeskyQR2
         if work is not None:
             stats_for.qr_stats_emitted(q)
         return _PendingQR(q, packed, K)

@@ -69,11 +69,14 @@ struct FusedFinalize {
   void* out;      // float64, or float32 when out_f32
   long long ldo;
   int out_f32;
-  // optional (K <= 32): column statistics of the OUTPUT taken as the operand of the following A.dot --
-  // per-CTA partials [gridDim.x][3][K] = max|out rowscale|, max|out rowscale rowa|, sum rowshift out (the layout
-  // colstats_partial_kernel writes) and the CTA count, so the next product needs no pass over its operand for them
+  // optional (K <= 32): column statistics of the OUTPUT taken as the operand of the following A.dot -- per-CTA partials
+  // [gridDim.x][3][K] = max|out rowscale|, max|out rowscale rowa|, sum rowshift out (the layout colstats_partial_kernel
+  // writes); the last CTA to finish folds them into stats_final (multiplier for stats_lim, its inverse, shift, maxima:
+  // what colstats_finish_kernel writes), so the next product needs no pass over its operand and no finish launch
   double* stats_partial;
-  double* stats_nblocks;
+  double* stats_final;
+  double stats_lim;
+  unsigned int* stats_ticket;   // device counter, zero between launches
 };
 
 #ifdef LMDEC_TRACE
@@ -355,7 +358,47 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
       out[K + k] = m2;
       out[2 * K + k] = ws;
     }
-    if (blockIdx.x == 0 && k == 0) *p.fz.stats_nblocks = (double)gridDim.x;
+    // the last CTA to get here folds all partial rows (block order) into the final statistics
+    __threadfence();
+    asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
+    if (k == 0) stats_acc[0] = atomicAdd(p.fz.stats_ticket, 1u) == gridDim.x - 1 ? 1.0 : 0.0;
+    asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
+    if (stats_acc[0] != 0.0) {
+      __threadfence();
+      // thread (slice, column) folds the rows slice, slice + n_sl, ...; thread `column` then folds the slices in order
+      asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
+      const int n_sl = kStatThreads / K, kc = k % K, sl = k / K;
+      if (sl < n_sl) {
+        double m1 = 0.0, m2 = 0.0, ws = 0.0;
+        for (unsigned b = sl; b < gridDim.x; b += n_sl) {
+          const double* in = p.fz.stats_partial + (size_t)b * 3 * K;
+          m1 = fmax(m1, __ldcg(in + kc));
+          m2 = fmax(m2, __ldcg(in + K + kc));
+          ws += __ldcg(in + 2 * K + kc);
+        }
+        stats_acc[(sl * 3 + 0) * K + kc] = m1;
+        stats_acc[(sl * 3 + 1) * K + kc] = m2;
+        stats_acc[(sl * 3 + 2) * K + kc] = ws;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
+      if (k < K) {
+        double m1 = 0.0, m2 = 0.0, ws = 0.0;
+        for (int j = 0; j < n_sl; ++j) {
+          m1 = fmax(m1, stats_acc[(j * 3 + 0) * K + k]);
+          m2 = fmax(m2, stats_acc[(j * 3 + 1) * K + k]);
+          ws += stats_acc[(j * 3 + 2) * K + k];
+        }
+        const double s_ = fmax(m1, m2);
+        const double mult = s_ > 0.0 ? p.fz.stats_lim / s_ : 1.0;   // as colstats_finish_kernel
+        double* st = p.fz.stats_final;
+        st[k] = mult;
+        st[K + k] = 1.0 / mult;
+        st[2 * K + k] = -ws;
+        st[3 * K + k] = m1;
+        st[4 * K + k] = m2;
+      }
+      if (k == 0) *p.fz.stats_ticket = 0u;
+    }
   }
 }
 

@@ -34,6 +34,7 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_mma_events;
 static bool g_mma_timing = false;
 static int g_sm_reserve = 0;
 static int g_pair_min_chunks = 64;
+__device__ unsigned int g_stats_ticket = 0;   // geno_mma's last-CTA fold of the output statistics (zero between launches)
 static int g_issuer_groups = 2;   // single-tile work items: issuer pairs taking alternate chunks (1 = one pair)
 static int g_prod_groups2 = 1;
 static int g_pair_mode = 1;   // lmdec_set_pair_mode: 0 disables the two-tiles-per-B-stage schedule (A/B tests)  // SMs left free for concurrently running collectives (row-sharded runs)
@@ -342,10 +343,8 @@ __global__ void __launch_bounds__(256) colstats_partial_kernel(const TB* __restr
                                                                int64_t kd_limit, int K, const double* __restrict__ row1,
                                                                const double* __restrict__ row2,
                                                                const double* __restrict__ w, int use_w,
-                                                               double* __restrict__ partial,
-                                                               double* __restrict__ n_blocks_out) {
+                                                               double* __restrict__ partial) {
   extern __shared__ double sm[];
-  if (n_blocks_out && blockIdx.x == 0 && threadIdx.x == 0) *n_blocks_out = (double)gridDim.x;
   const int k = threadIdx.x % K, ry = threadIdx.x / K, rpb = blockDim.x / K;
   double m1 = 0.0, m2 = 0.0, ws = 0.0;
   if (ry < rpb) {
@@ -393,13 +392,10 @@ __global__ void __launch_bounds__(256) colstats_partial_kernel(const TB* __restr
 }
 // stats layout: [0,K) mult, [K,2K) 1/mult, [2K,3K) shift = shift_sign * wsum, [3K,4K) amax, [4K,5K) amax2
 // 1024 threads: thread (slice, k) folds blocks slice, slice+S, ... ; thread k then folds the slices in order.
-// n_blocks < 0: the count is read from n_blocks_dev (partials emitted by an earlier launch).
 __global__ void __launch_bounds__(1024) colstats_finish_kernel(const double* __restrict__ partial, int n_blocks, int K,
                                                                double lim, double shift_sign,
-                                                               double* __restrict__ stats,
-                                                               const double* __restrict__ n_blocks_dev) {
+                                                               double* __restrict__ stats) {
   extern __shared__ double sm[];
-  if (n_blocks < 0) n_blocks = (int)*n_blocks_dev;
   const int n_sl = blockDim.x / K;
   const int k = threadIdx.x % K, sl = threadIdx.x / K;
   double m1 = 0.0, m2 = 0.0, ws = 0.0;
@@ -786,7 +782,7 @@ __device__ void cqr_apply(const double* __restrict__ in, int rows, int K, const 
 __global__ void __cluster_dims__(kCqrCluster, 1, 1) __launch_bounds__(kCqrThreads)
     cholqr2_small_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int K, int per, double rank_tol,
                          double* __restrict__ Q, int64_t ldq, double* __restrict__ packed,
-                         double* __restrict__ stats_work) {
+                         double* __restrict__ stats_work, double stats_lim) {
   extern __shared__ double cqr_sm[];
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -870,12 +866,10 @@ __global__ void __cluster_dims__(kCqrCluster, 1, 1) __launch_bounds__(kCqrThread
         m1 = fmax(m1, pacc[j * K + t]);
         ws += pacc[kCqrThreads + j * K + t];
       }
-      double* out = stats_work + 5 * K + 1 + (size_t)rank * 3 * K;
+      double* out = stats_work + 5 * K + (size_t)rank * 2 * K;
       out[t] = m1;
-      out[K + t] = 0.0;
-      out[2 * K + t] = ws;
+      out[K + t] = ws;
     }
-    if (rank == 0 && t == 0) stats_work[5 * K] = (double)kCqrCluster;
   }
   if (rank == 0) {
     for (int i = t; i < kk; i += kCqrThreads) {
@@ -893,6 +887,21 @@ __global__ void __cluster_dims__(kCqrCluster, 1, 1) __launch_bounds__(kCqrThread
     }
   }
   cluster.sync();   // peers may still be reading this CTA's part2
+  if (stats_work && rank == 0 && t < K) {
+    // fold the CTAs' rows into the final statistics (what colstats_finish_kernel writes)
+    double m1 = 0.0, ws = 0.0;
+    for (int c = 0; c < kCqrCluster; ++c) {
+      const double* in = stats_work + 5 * K + (size_t)c * 2 * K;
+      m1 = fmax(m1, __ldcg(in + t));
+      ws += __ldcg(in + K + t);
+    }
+    const double mult = m1 > 0.0 ? stats_lim / m1 : 1.0;
+    stats_work[t] = mult;
+    stats_work[K + t] = 1.0 / mult;
+    stats_work[2 * K + t] = -ws;
+    stats_work[3 * K + t] = m1;
+    stats_work[4 * K + t] = 0.0;
+  }
   if (t == 0) LMDEC_STAMP(7, 16);
 }
 
@@ -1155,7 +1164,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
     p.fz = *fz;
     p.fuse = 1;
     if (fz->stats_partial) {
-      if (K <= 32 && fz->stats_nblocks) p.fuse = 2;   // epilogue also emits the output's column statistics
+      if (K <= 32 && fz->stats_final) p.fuse = 2;   // epilogue also emits the output's column statistics
       else p.fz.stats_partial = nullptr;
     }
     if (fused) *fused = true;
@@ -1283,12 +1292,13 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
   return check_launch("lmdec_sqdiff", 2);
 }
 
-int64_t lmdec_apply_work_doubles(int K) { return (int64_t)5 * K + 1 + (int64_t)kStatsMaxBlocks * 3 * K; }
+int64_t lmdec_apply_work_doubles(int K) { return (int64_t)5 * K + (int64_t)kStatsMaxBlocks * 3 * K; }
 
-// column statistics of a float64 / float32 operand -> partial rows (+ their count in *n_blocks_out when given)
-static int launch_colstats_partial(const void* B, bool b_f32, int64_t ldb, int64_t kd_limit, int K, const double* row1,
-                                   const double* row2, const double* w, int use_w, double* partial,
-                                   double* n_blocks_out, cudaStream_t st, int* blocks_out) {
+// column statistics of a float64 / float32 operand: partial rows, then the fold into stats (multiplier for `lim`, its
+// inverse, rank-1 shift, maxima)
+static int launch_colstats(const void* B, bool b_f32, int64_t ldb, int64_t kd_limit, int K, const double* row1,
+                           const double* row2, const double* w, int use_w, double lim, double* stats, double* partial,
+                           cudaStream_t st) {
   const int rpb = 256 / K > 0 ? 256 / K : 1;
   int64_t blocks = cdiv(kd_limit, (int64_t)rpb * 8);
   if (blocks > kStatsMaxBlocks) blocks = kStatsMaxBlocks;
@@ -1296,12 +1306,13 @@ static int launch_colstats_partial(const void* B, bool b_f32, int64_t ldb, int64
   const int threads = 256;
   if (b_f32)
     colstats_partial_kernel<float><<<(unsigned)blocks, threads, 3 * threads * sizeof(double), st>>>(
-        (const float*)B, ldb, kd_limit, K, row1, row2, w, use_w, partial, n_blocks_out);
+        (const float*)B, ldb, kd_limit, K, row1, row2, w, use_w, partial);
   else
     colstats_partial_kernel<double><<<(unsigned)blocks, threads, 3 * threads * sizeof(double), st>>>(
-        (const double*)B, ldb, kd_limit, K, row1, row2, w, use_w, partial, n_blocks_out);
-  if (blocks_out) *blocks_out = (int)blocks;
-  return 0;
+        (const double*)B, ldb, kd_limit, K, row1, row2, w, use_w, partial);
+  colstats_finish_kernel<<<1, 1024, (size_t)(1024 / K) * 3 * K * sizeof(double), st>>>(partial, (int)blocks, K, lim, -1.0,
+                                                                                          stats);
+  return check_launch("lmdec_operator_apply (colstats)", 2);
 }
 
 int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
@@ -1315,7 +1326,7 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
   const bool b_f32 = (transpose_flags & 4) != 0;          // B is float32 (else float64)
   const bool out_f32 = (transpose_flags & 8) != 0;        // out is float32 (else float64)
   const bool emit_stats = (transpose_flags & 16) != 0;    // A^T y only: leave out's column statistics in work
-  const bool stats_ready = (transpose_flags & 32) != 0;   // A t only: B's column statistics are already in work
+  const bool stats_ready = (transpose_flags & 32) != 0;   // B's column statistics are already in work
   const int N = (K * P + 15) / 16 * 16;
   if (N > 128) return fail("lmdec_operator_apply: K*P needs more than 128 tensor-core columns");
   if (has_missing && !impute) return fail("lmdec_operator_apply: has_missing needs the imputation vector");
@@ -1325,21 +1336,17 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
     return fail("lmdec_operator_apply: flag 16 goes with A.T.dot, flag 32 excludes flag 2");
   cudaStream_t st = (cudaStream_t)stream;
   double* stats = work;
-  double* n_blocks_dev = work + 5 * K;
-  double* partial = work + 5 * K + 1;
+  double* partial = work + 5 * K;
   const bool two = has_missing && !transpose;
   // ---- column statistics -> fixed-point multiplier and rank-1 shift
   const double lim = ldexp(1.0, 8 * P - (two ? 3 : 2));
   int rc = 0;
   if (!reuse_operand) {
-    int blocks = -1;
-    if (!stats_ready)
-      launch_colstats_partial(B, b_f32, ldb, kd_limit, K, transpose ? nullptr : scale, two ? impute : nullptr,
-                              transpose ? nullptr : center_w, center_w != nullptr, partial, nullptr, st, &blocks);
-    colstats_finish_kernel<<<1, 1024, (size_t)(1024 / K) * 3 * K * sizeof(double), st>>>(partial, blocks, K, lim, -1.0,
-                                                                                            stats, n_blocks_dev);
-    rc = check_launch("lmdec_operator_apply (colstats)", stats_ready ? 1 : 2);
-    if (rc) return rc;
+    if (!stats_ready) {
+      rc = launch_colstats(B, b_f32, ldb, kd_limit, K, transpose ? nullptr : scale, two ? impute : nullptr,
+                           transpose ? nullptr : center_w, center_w != nullptr, lim, stats, partial, st);
+      if (rc) return rc;
+    }
     // ---- int8 planes
     rc = b_f32 ? quantize_planes_t<float>((const float*)B, ldb, Kd, kd_limit, K, P, N, stats,
                                           transpose ? nullptr : scale, two ? impute : nullptr, image1,
@@ -1350,6 +1357,11 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
     if (rc) return rc;
   }
   // ---- tensor-core product, with the diagonal / rank-1 terms fused into its epilogue when it is not split
+  static thread_local unsigned int* ticket = nullptr;
+  if (emit_stats && !ticket && cudaGetSymbolAddress((void**)&ticket, g_stats_ticket) != cudaSuccess)
+    return fail("lmdec_operator_apply: cudaGetSymbolAddress");
+  // the following A.dot quantises `out` with has_missing ? 8P-3 : 8P-2 bits below its column maximum
+  const double lim_next = ldexp(1.0, 8 * P - (has_missing ? 3 : 2));
   FusedFinalize fz;
   fz.colscale = stats + K;
   fz.colshift = center_w ? stats + 2 * K : nullptr;
@@ -1360,7 +1372,9 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
   fz.ldo = ldo;
   fz.out_f32 = out_f32 ? 1 : 0;
   fz.stats_partial = emit_stats ? partial : nullptr;
-  fz.stats_nblocks = emit_stats ? n_blocks_dev : nullptr;
+  fz.stats_final = emit_stats ? stats : nullptr;    // (the kernel has read its own colscale / colshift by then)
+  fz.stats_lim = lim_next;
+  fz.stats_ticket = ticket;
   bool fused = false, emitted = false;
   rc = launch_geno_mma(store, M, Kd, m_limit, kd_limit, has_missing, (transpose && has_missing) ? 1 : 0, image1,
                        two ? image2 : nullptr, K, P, N, acc0, (transpose && has_missing) ? acc1 : nullptr, 0, stream,
@@ -1378,12 +1392,10 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
     }
     if (rc) return rc;
   }
-  if (emit_stats && !emitted) {
+  if (emit_stats && !emitted)
     // the epilogue could not take the statistics along (split contraction or K > 32): one pass over out
-    launch_colstats_partial(out, out_f32, ldo, m_limit, K, scale, has_missing ? impute : nullptr, center_w,
-                            center_w != nullptr, partial, n_blocks_dev, st, nullptr);
-    rc = check_launch("lmdec_operator_apply (output colstats)");
-  }
+    rc = launch_colstats(out, out_f32, ldo, m_limit, K, scale, has_missing ? impute : nullptr, center_w,
+                         center_w != nullptr, lim_next, stats, partial, st);
   return rc;
 }
 
@@ -1454,7 +1466,7 @@ int lmdec_gram_chol(const double* X, int64_t ldx, int64_t m, int K, double rank_
 int64_t lmdec_cholqr2_small_max_elems(void) { return (int64_t)kCqrCluster * kCqrSliceDoubles; }
 
 int lmdec_cholqr2_small(const double* X, int64_t ldx, int64_t n, int K, double rank_tol, double* Q, int64_t ldq,
-                        double* packed, double* stats_work, void* stream) {
+                        double* packed, double* stats_work, double stats_lim, void* stream) {
   if (K < 1 || K > 32) return fail("lmdec_cholqr2_small: K out of range (1..32)");
   if (n < 1 || Q == X) return fail("lmdec_cholqr2_small: needs n >= 1 and an output distinct from the input");
   const int64_t per = (n + kCqrCluster - 1) / kCqrCluster;
@@ -1466,7 +1478,7 @@ int lmdec_cholqr2_small(const double* X, int64_t ldx, int64_t n, int K, double r
     attr_set = true;
   }
   cholqr2_small_kernel<<<kCqrCluster, kCqrThreads, smem, (cudaStream_t)stream>>>(X, ldx, n, K, (int)per, rank_tol, Q,
-                                                                                 ldq, packed, stats_work);
+                                                                                 ldq, packed, stats_work, stats_lim);
   return check_launch("lmdec_cholqr2_small");
 }
 

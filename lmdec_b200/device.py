@@ -237,15 +237,16 @@ def cholqr2_small_fits(n: int, K: int) -> bool:
     return K <= 32 and per * K * 8 <= _capi.load().lmdec_cholqr2_small_max_elems()
 
 
-def cholqr2_small(x: torch.Tensor, rank_tol: float = 1e-12, stats_work: torch.Tensor = None):
+def cholqr2_small(x: torch.Tensor, rank_tol: float = 1e-12, stats_work: torch.Tensor = None, stats_lim: float = 0.0):
     """CholeskyQR2 of a small local iterate in one launch: (q, packed) with packed = [r | flag1 | flag2 | dev].
-    `stats_work`: work buffer of the operator that multiplies A^T by q next (receives q's column statistics)."""
+    `stats_work` / `stats_lim`: work buffer of the operator that multiplies A^T by q next (receives q's column
+    statistics) and its fixed-point range 2^(8 planes - 2)."""
     lib = _capi.load()
     x = _rows(x)
     n, K = x.shape
     q = torch.empty((n, K), dtype=F64, device=x.device)
     packed = torch.empty(K * K + 3, dtype=F64, device=x.device)
     _capi.check(lib.lmdec_cholqr2_small(_capi.ptr(x), x.stride(0), n, K, float(rank_tol), _capi.ptr(q), K,
-                                        _capi.ptr(packed), _capi.ptr(stats_work), _capi.stream_ptr()),
+                                        _capi.ptr(packed), _capi.ptr(stats_work), float(stats_lim), _capi.stream_ptr()),
                 "lmdec_cholqr2_small")
     return q, packed

@@ -400,13 +400,13 @@ class GenotypeOperator:
         return out
 
     def qr_stats_slot(self, rows: int, K: int):
-        """Work buffer that may receive the column statistics of the iterate q [rows, K] from the orthonormalisation
-        kernel (lmdec_cholqr2_small), or None when the following A^T q cannot use them."""
+        """(work buffer, fixed-point range) for the column statistics of the iterate q [rows, K] that the
+        orthonormalisation kernel (lmdec_cholqr2_small) can leave for the following A^T q; (None, 0) when it cannot."""
         if not _FUSED_STATS or self.store.group is not None or rows != self.rows or _round16(K * self.planes) > 128:
-            return None
+            return None, 0.0
         buf = self._buffers(K)
         buf.pop("emitted", None)
-        return buf["work"]
+        return buf["work"], float(2 ** (8 * self.planes - 2))
 
     def qr_stats_emitted(self, q: torch.Tensor):
         self._buffers(q.shape[1])["emitted"] = ("q", weakref.ref(q), q._version)
