@@ -172,6 +172,13 @@ int lmdec_gram_chol(const double* X, int64_t ldx, int64_t m, int K, double rank_
 int64_t lmdec_cholqr2_small_max_elems(void);
 int lmdec_cholqr2_small(const double* X, int64_t ldx, int64_t n, int K, double rank_tol, double* Q, int64_t ldq,
                         double* packed, double* stats_work, double stats_lim, void* stream);
+/* The same CholeskyQR2 for mid-size local iterates (K <= 32, n*K <= lmdec_cholqr2_grid_max_elems() = SMs * 16384) in one
+ * COOPERATIVE launch over all SMs (row slices in shared memory, Gram partials through global memory, grid-wide syncs).
+ * gwork: lmdec_cholqr2_grid_work_doubles(K) doubles of scratch.  Outputs as lmdec_cholqr2_small.  */
+int64_t lmdec_cholqr2_grid_max_elems(void);
+int64_t lmdec_cholqr2_grid_work_doubles(int K);
+int lmdec_cholqr2_grid(const double* X, int64_t ldx, int64_t n, int K, double rank_tol, double* Q, int64_t ldq,
+                       double* packed, double* gwork, double* stats_work, double stats_lim, void* stream);
 /* packed[0..K*K) = r2 r1, then flag1, flag2, max|g2 - I|: what the host reads back from one CholeskyQR2. */
 int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const int* flag1, const int* flag2, int K,
                   double* packed, void* stream);

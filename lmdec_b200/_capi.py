@@ -36,6 +36,9 @@ SIGNATURES = {
     "lmdec_chol_whiten": (_i32, [_p, _i32, C.c_double, _p, _p, _p, _p]),
     "lmdec_gram_chol": (_i32, [_p, _i64, _i64, _i32, C.c_double, _p, _p, _p, _p, _p, _p]),
     "lmdec_cholqr2_small_max_elems": (_i64, []),
+    "lmdec_cholqr2_grid_max_elems": (_i64, []),
+    "lmdec_cholqr2_grid_work_doubles": (_i64, [_i32]),
+    "lmdec_cholqr2_grid": (_i32, [_p, _i64, _i64, _i32, C.c_double, _p, _i64, _p, _p, _p, C.c_double, _p]),
     "lmdec_cholqr2_small": (_i32, [_p, _i64, _i64, _i32, C.c_double, _p, _i64, _p, _p, C.c_double, _p]),
     "lmdec_qr_pack": (_i32, [_p, _p, _p, _p, _p, _i32, _p, _p]),
     "lmdec_kernel_timing": (None, [_i32]),

@@ -13,7 +13,8 @@ import os
 import numpy as np
 import torch
 
-from ..device import F64, chol_whiten, cholqr2_small, cholqr2_small_fits, gram, gram_chol, qr_pack
+from ..device import (F64, chol_whiten, cholqr2_grid, cholqr2_grid_fits, cholqr2_small, cholqr2_small_fits, gram,
+                      gram_chol, qr_pack)
 
 
 def _allreduce(t: torch.Tensor, group):
@@ -134,13 +135,16 @@ def orthonormalize_begin(x: torch.Tensor, group=None, stats_for=None) -> _Pendin
     the caller can queue the next products behind it before asking for r.  `stats_for`: the operator whose A^T product
     consumes q next; when it offers `qr_stats_slot`, the single-launch kernel leaves q's column statistics there."""
     K = x.shape[1]
-    if group is None and x.dtype == F64 and _SMALL_QR and cholqr2_small_fits(x.shape[0], K):
-        slot = getattr(stats_for, "qr_stats_slot", None)
-        work, lim = slot(x.shape[0], K) if slot is not None else (None, 0.0)
-        q, packed = cholqr2_small(x, stats_work=work, stats_lim=lim)  # one launch for the whole CholeskyQR2
-        if work is not None:
-            stats_for.qr_stats_emitted(q)
-        return _PendingQR(q, packed, K)
+    if group is None and x.dtype == F64 and _SMALL_QR and K <= 32:
+        small = cholqr2_small_fits(x.shape[0], K)
+        if small or cholqr2_grid_fits(x.shape[0], K):
+            slot = getattr(stats_for, "qr_stats_slot", None)
+            work, lim = slot(x.shape[0], K) if slot is not None else (None, 0.0)
+            # one launch for the whole CholeskyQR2: one 8-CTA cluster, or all SMs cooperatively for mid-size iterates
+            q, packed = (cholqr2_small if small else cholqr2_grid)(x, stats_work=work, stats_lim=lim)
+            if work is not None:
+                stats_for.qr_stats_emitted(q)
+            return _PendingQR(q, packed, K)
     if group is None:
         _, ri1, r1, f1 = gram_chol(x)                  # 2 launches per pass, nothing else
         q1 = x @ ri1

@@ -905,6 +905,185 @@ __global__ void __cluster_dims__(kCqrCluster, 1, 1) __launch_bounds__(kCqrThread
   if (t == 0) LMDEC_STAMP(7, 16);
 }
 
+// in-place capable variant of cqr_apply: every warp reads its 8-row tile completely (all column tiles) before it
+// writes it, so `out` may alias `in` (ldo == K)
+__device__ void cqr_apply_rows(const double* in, int rows, int K, const double* __restrict__ r_inv, double* out,
+                               int64_t ldo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = lane & 3, i = lane >> 2;
+  const int nt = (K + 7) >> 3, mt = (rows + 7) >> 3;
+  for (int tm = warp; tm < mt; tm += kCqrWarps) {
+    const int r = tm * 8 + i;
+    const bool okr = r < rows;
+    const double* row = in + (size_t)r * K;
+    double c[4][2];
+#pragma unroll
+    for (int tb = 0; tb < 4; ++tb) {
+      c[tb][0] = c[tb][1] = 0.0;
+      if (tb < nt) {
+        const int b = tb * 8 + i;
+        const int ks = min((K + 3) >> 2, 2 * tb + 2);       // r_inv is upper triangular: rows a <= 8 tb + 7 only
+#pragma unroll
+        for (int s_ = 0; s_ < 8; ++s_) {
+          if (s_ < ks) {
+            const int a = 4 * s_ + j;
+            dmma884(c[tb][0], c[tb][1], (okr && a < K) ? row[a] : 0.0, (a < K && b < K) ? r_inv[a * K + b] : 0.0);
+          }
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int tb = 0; tb < 4; ++tb) {
+      const int b = tb * 8 + 2 * j;
+      if (tb < nt && okr) {
+        if (b < K) out[(int64_t)r * ldo + b] = c[tb][0];
+        if (b + 1 < K) out[(int64_t)r * ldo + b + 1] = c[tb][1];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+constexpr int kGridSliceDoubles = 16384;   // per-CTA row slice (one buffer, the first pass is applied in place)
+
+// CholeskyQR2 of a mid-size iterate (K <= 32, n*K <= SMs * 16384) in ONE cooperative launch over all SMs: the row slice of
+// a CTA stays in shared memory for both passes; per pass the K x K Gram partials go through global memory -- element e is
+// summed over the CTAs (fixed order) by CTA e % grid, then broadcast -- with two grid syncs.  Same algorithm, outputs and
+// failure flags as cholqr2_small_kernel.  gwork: [grid][K*K] partials | [2][K*K] sums | [grid][2K] statistics rows.
+__global__ void __launch_bounds__(kCqrThreads)
+    cholqr2_grid_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int K, int per, double rank_tol,
+                        double* __restrict__ Q, int64_t ldq, double* __restrict__ packed, double* __restrict__ gwork,
+                        double* __restrict__ stats_work, double stats_lim) {
+  extern __shared__ double cqr_sm[];
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  const int rank = blockIdx.x, G_ = gridDim.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int kk = K * K;
+  double* buf = cqr_sm;                     // [per][K] row slice: X, then Q1 (in place)
+  double* part = buf + (size_t)per * K;
+  double* pacc = part + kk;                 // [warps][8][8] partial Gram tiles
+  double* Gm = pacc + kCqrPaccDoubles;
+  double* Lsm = Gm + kk;
+  double* Lf = Lsm + kk;
+  double* vec = Lf + kk;                    // [4][K]
+  double* ri = vec + 4 * K;
+  double* r1 = ri + kk;
+  double* r2 = r1 + kk;
+  double* gpart = gwork;
+  double* gsum = gwork + (size_t)G_ * kk;
+  double* gstat = gsum + 2 * kk;
+  __shared__ int flags[2];
+  __shared__ double red[kCqrThreads / 32];
+  const int64_t row0 = (int64_t)rank * per;
+  const int rows = (int)max((int64_t)0, min((int64_t)per, n - row0));
+  for (int i = t; i < rows * K; i += kCqrThreads) {
+    const int r = i / K, c = i - r * K;
+    buf[i] = X[(row0 + r) * ldx + c];
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 2; ++pass) {
+    cqr_gram_local(buf, rows, K, pacc, part);
+    __syncthreads();
+    for (int i = t; i < kk; i += kCqrThreads) gpart[(size_t)rank * kk + i] = part[i];
+    grid.sync();
+    // element e of the Gram matrix: warp (e / grid) of CTA e % grid sums the grid's partials, lane-strided then butterfly
+    for (int e = rank + warp * G_; e < kk; e += kCqrWarps * G_) {
+      double acc = 0.0;
+      for (int b = lane; b < G_; b += 32) acc += __ldcg(gpart + (size_t)b * kk + e);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) gsum[pass * kk + e] = acc;
+    }
+    grid.sync();
+    for (int i = t; i < kk; i += kCqrThreads) Gm[i] = __ldcg(gsum + pass * kk + i);
+    __syncthreads();
+    if (pass == 1) {   // deviation of the second Gram matrix from the identity (health check of the first pass)
+      double dev = 0.0;
+      for (int i = t; i < kk; i += kCqrThreads) {
+        const double g = Gm[i] - ((i / K) == (i % K) ? 1.0 : 0.0);
+        dev = fmax(dev, g == g ? fabs(g) : INFINITY);
+      }
+      for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+      if (lane == 0) red[warp] = dev;
+    }
+    const int f = block_chol(Gm, K, rank_tol, Lsm, Lf, vec, ri, pass ? r2 : r1);
+    if (t == 0) flags[pass] = f;
+    if (pass == 0) cqr_apply_rows(buf, rows, K, ri, buf, K);
+    else cqr_apply_rows(buf, rows, K, ri, Q + row0 * ldq, ldq);
+    __syncthreads();
+  }
+  if (stats_work) {
+    // column statistics of Q for the A^T q that follows (see cholqr2_small_kernel): one row per CTA, CTA 0 folds them
+    const int n_sl = kCqrThreads / K;
+    const int k = t % K, sl = t / K;
+    if (sl < n_sl) {
+      double m1 = 0.0, ws = 0.0;
+      for (int r = sl; r < rows; r += n_sl) {
+        const double y = Q[(row0 + r) * ldq + k];
+        double v = fabs(y);
+        if (v != v) v = INFINITY;
+        m1 = fmax(m1, v);
+        ws += y;
+      }
+      pacc[sl * K + k] = m1;
+      pacc[kCqrThreads + sl * K + k] = ws;
+    }
+    __syncthreads();
+    if (t < K) {
+      double m1 = 0.0, ws = 0.0;
+      for (int j = 0; j < n_sl; ++j) {
+        m1 = fmax(m1, pacc[j * K + t]);
+        ws += pacc[kCqrThreads + j * K + t];
+      }
+      gstat[(size_t)rank * 2 * K + t] = m1;
+      gstat[(size_t)rank * 2 * K + K + t] = ws;
+    }
+    grid.sync();
+    if (rank == 0) {
+      const int k2 = t % K, sl2 = t / K;
+      if (sl2 < n_sl) {
+        double m1 = 0.0, ws = 0.0;
+        for (int b = sl2; b < G_; b += n_sl) {
+          m1 = fmax(m1, __ldcg(gstat + (size_t)b * 2 * K + k2));
+          ws += __ldcg(gstat + (size_t)b * 2 * K + K + k2);
+        }
+        pacc[sl2 * K + k2] = m1;
+        pacc[kCqrThreads + sl2 * K + k2] = ws;
+      }
+      __syncthreads();
+      if (t < K) {
+        double m1 = 0.0, ws = 0.0;
+        for (int j = 0; j < n_sl; ++j) {
+          m1 = fmax(m1, pacc[j * K + t]);
+          ws += pacc[kCqrThreads + j * K + t];
+        }
+        const double mult = m1 > 0.0 ? stats_lim / m1 : 1.0;
+        stats_work[t] = mult;
+        stats_work[K + t] = 1.0 / mult;
+        stats_work[2 * K + t] = -ws;
+        stats_work[3 * K + t] = m1;
+        stats_work[4 * K + t] = 0.0;
+      }
+    }
+  }
+  if (rank == 0) {
+    for (int i = t; i < kk; i += kCqrThreads) {
+      const int a = i / K, b = i - a * K;
+      double acc = 0.0;
+      for (int c = a; c <= b; ++c) acc += r2[a * K + c] * r1[c * K + b];
+      packed[i] = acc;
+    }
+    if (t == 0) {
+      double m = 0.0;
+      for (int i = 0; i < kCqrThreads / 32; ++i) m = fmax(m, red[i]);
+      packed[kk] = (double)flags[0];
+      packed[kk + 1] = (double)flags[1];
+      packed[kk + 2] = m;
+    }
+  }
+}
+
 __global__ void qvals_kernel(const double* __restrict__ si, const double* __restrict__ sj, int k, int scale,
                              double* __restrict__ out) {
   double d = 0, a = 0, b = 0;
@@ -1480,6 +1659,45 @@ int lmdec_cholqr2_small(const double* X, int64_t ldx, int64_t n, int K, double r
   cholqr2_small_kernel<<<kCqrCluster, kCqrThreads, smem, (cudaStream_t)stream>>>(X, ldx, n, K, (int)per, rank_tol, Q,
                                                                                  ldq, packed, stats_work, stats_lim);
   return check_launch("lmdec_cholqr2_small");
+}
+
+static int sm_count() {
+  static thread_local int n_sm = -1;
+  if (n_sm < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n_sm = 0;
+  }
+  return n_sm;
+}
+
+int64_t lmdec_cholqr2_grid_max_elems(void) { return (int64_t)sm_count() * kGridSliceDoubles; }
+int64_t lmdec_cholqr2_grid_work_doubles(int K) { return (int64_t)(sm_count() + 2) * K * K + (int64_t)sm_count() * 2 * K; }
+
+int lmdec_cholqr2_grid(const double* X, int64_t ldx, int64_t n, int K, double rank_tol, double* Q, int64_t ldq,
+                       double* packed, double* gwork, double* stats_work, double stats_lim, void* stream) {
+  if (K < 1 || K > 32) return fail("lmdec_cholqr2_grid: K out of range (1..32)");
+  if (n < 1 || Q == X || !gwork) return fail("lmdec_cholqr2_grid: needs n >= 1, an output distinct from the input, gwork");
+  const int n_sm = sm_count();
+  if (n_sm < 1) return fail("lmdec_cholqr2_grid: no CUDA device");
+  int64_t grid = cdiv(n, 8);
+  if (grid > n_sm) grid = n_sm;
+  int64_t per = (cdiv(n, grid) + 7) / 8 * 8;      // 8-row DMMA tiles never straddle CTAs
+  grid = cdiv(n, per);
+  if (per * K > kGridSliceDoubles) return fail("lmdec_cholqr2_grid: iterate too large (see lmdec_cholqr2_grid_max_elems)");
+  const size_t smem = ((size_t)per * K + 9 * K * K + 4 * K + kCqrPaccDoubles) * sizeof(double);
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(cholqr2_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    attr_set = true;
+  }
+  int per_i = (int)per;
+  void* args[] = {(void*)&X, (void*)&ldx, (void*)&n, (void*)&K, (void*)&per_i, (void*)&rank_tol, (void*)&Q,
+                  (void*)&ldq, (void*)&packed, (void*)&gwork, (void*)&stats_work, (void*)&stats_lim};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)cholqr2_grid_kernel, dim3((unsigned)grid), dim3(kCqrThreads),
+                                              args, smem, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail("lmdec_cholqr2_grid: cooperative launch: %s", cudaGetErrorString(e));
+  return check_launch("lmdec_cholqr2_grid");
 }
 
 int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const int* flag1, const int* flag2, int K,

@@ -250,3 +250,27 @@ def cholqr2_small(x: torch.Tensor, rank_tol: float = 1e-12, stats_work: torch.Te
                                         _capi.ptr(packed), _capi.ptr(stats_work), float(stats_lim), _capi.stream_ptr()),
                 "lmdec_cholqr2_small")
     return q, packed
+
+
+def cholqr2_grid_fits(n: int, K: int) -> bool:
+    lib = _capi.load()
+    sms = lib.lmdec_cholqr2_grid_max_elems() // 16384
+    if K > 32 or sms < 1:
+        return False
+    grid = min(sms, -(-n // 8))
+    per = -(-(-(-n // grid)) // 8) * 8
+    return per * K <= 16384
+
+
+def cholqr2_grid(x: torch.Tensor, rank_tol: float = 1e-12, stats_work: torch.Tensor = None, stats_lim: float = 0.0):
+    """CholeskyQR2 of a mid-size local iterate in one cooperative launch over all SMs: (q, packed) as cholqr2_small."""
+    lib = _capi.load()
+    x = _rows(x)
+    n, K = x.shape
+    q = torch.empty((n, K), dtype=F64, device=x.device)
+    packed = torch.empty(K * K + 3, dtype=F64, device=x.device)
+    gwork = _work(x.device, lib.lmdec_cholqr2_grid_work_doubles(K))
+    _capi.check(lib.lmdec_cholqr2_grid(_capi.ptr(x), x.stride(0), n, K, float(rank_tol), _capi.ptr(q), K,
+                                       _capi.ptr(packed), _capi.ptr(gwork), _capi.ptr(stats_work), float(stats_lim),
+                                       _capi.stream_ptr()), "lmdec_cholqr2_grid")
+    return q, packed

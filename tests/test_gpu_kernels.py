@@ -262,3 +262,35 @@ def test_cholqr2_small_flags_rank_deficiency(cuda):
     _, packed = cholqr2_small(xd)
     packed = packed.cpu().numpy()
     assert packed[36] != 0 or packed[37] != 0 or not packed[38] < 1e-2
+
+
+@pytest.mark.parametrize("n,K", [(10000, 20), (12500, 20), (61000, 30), (50, 3), (2504, 20), (70001, 32)])
+def test_cholqr2_grid_cooperative_launch(cuda, n, K):
+    """Mid-size iterates: the all-SM cooperative CholeskyQR2 gives Q^T Q = I, Q R = X, the R of Householder QR, and the
+    column statistics of Q for the product that follows."""
+    import torch
+    from lmdec_b200.device import cholqr2_grid, cholqr2_grid_fits
+    capi, lib = _capi()
+    assert cholqr2_grid_fits(n, K)
+    rng = np.random.default_rng(n * 13 + K)
+    x = rng.standard_normal((n, K)) @ (np.eye(K) + 0.3 * rng.standard_normal((K, K))) * np.logspace(0, 3, K)
+    xd = torch.from_numpy(np.pad(x, ((0, 0), (0, 5)))).to(cuda)[:, :K]      # strided rows
+    work = torch.zeros(lib.lmdec_apply_work_doubles(K), dtype=torch.float64, device=cuda)
+    lim = float(2 ** 22)
+    q, packed = cholqr2_grid(xd, stats_work=work, stats_lim=lim)
+    q, packed, stats = q.cpu().numpy(), packed.cpu().numpy(), work[:5 * K].cpu().numpy()
+    r = packed[:K * K].reshape(K, K)
+    assert packed[K * K] == 0 and packed[K * K + 1] == 0 and packed[K * K + 2] < 1e-6
+    np.testing.assert_allclose(q.T @ q, np.eye(K), atol=1e-13)
+    np.testing.assert_allclose(q @ r, x, rtol=0, atol=1e-12 * np.abs(x).max())
+    rn = np.linalg.qr(x)[1]
+    np.testing.assert_allclose(r, rn * np.sign(np.diag(rn))[:, None], rtol=1e-8, atol=1e-10 * np.abs(rn).max())
+    amax = np.abs(q).max(axis=0)
+    assert np.array_equal(stats[3 * K:4 * K], amax) and np.array_equal(stats[:K], lim / amax)
+    np.testing.assert_allclose(stats[2 * K:3 * K], -q.sum(axis=0), rtol=0, atol=1e-12)
+    # non-finite input is flagged, not silently factorised
+    xd2 = xd.clone()
+    xd2[n // 2, K // 2] = float("inf")
+    _, packed2 = cholqr2_grid(xd2)
+    packed2 = packed2.cpu().numpy()
+    assert packed2[K * K] != 0 or packed2[K * K + 1] != 0 or not packed2[K * K + 2] < 1e-2
