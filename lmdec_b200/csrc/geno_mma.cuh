@@ -14,11 +14,14 @@
 //   warp  8     tile loader: one thread, cp.async.bulk (TMA engine) of whole 8 KB store tiles into an 8-deep smem ring
 //   warps 9-12  MMA issuers: one elected lane each.  A narrow-N tcgen05.mma is limited by the issuing thread (~45-54
 //               cycles per instruction, profiles/r01/umma_probe4_issuers.log), so the MMAs of a chunk are spread over
-//               several issuers, each owning one accumulator: 2 issuers = (value plane, indicator plane) with missing
-//               data or (even, odd K-blocks) without; 4 issuers in pair mode M = (tile, plane).
+//               several issuers, each owning one accumulator: an issuer pair = (value plane, indicator plane) with
+//               missing data or (even, odd K-blocks) without; pair mode M: 4 issuers = (tile, plane); single tiles: two
+//               issuer pairs on alternate chunks (the serial per-chunk barrier round trips of an issuing thread, not
+//               the tensor pipe, set the period: profiles/r01/pipeline_trace.txt).
 //   warps 13-20 epilogue (two per TMEM lane quarter, splitting the column groups): TMEM -> registers -> exact plane
 //               combine -> global (finalized float, int64 store, or int64 atomicAdd for split-K).  Short contractions
-//               alternate two accumulator sets, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//               alternate two accumulator sets, so the epilogue of tile i overlaps the MMAs of tile i+1.  For A^T q the
+//               epilogue also reduces the column statistics of its output for the A t that follows (kOutFusedStats).
 //   warp  21    B loader: one thread, cp.async.bulk of the pre-laid-out plane image into its own smem ring
 // Pair mode (long contractions): two m-tiles are processed against every staged chunk of the operand image, halving the
 // image's L2 -> SM traffic (it is re-read by every m-tile and dominates the product's on-chip traffic).
