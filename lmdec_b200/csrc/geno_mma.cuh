@@ -169,7 +169,7 @@ __device__ __forceinline__ void produce_chunk(const uint4 (&raw)[KB / 2], uint32
 //      3: as 2, plus the column statistics of the finalized output (FusedFinalize::stats_partial).
 enum { kOutStore = 0, kOutAtomic = 1, kOutFused = 2, kOutFusedStats = 3 };
 // Statistics accumulators (kOutFusedStats): every epilogue thread (= output row of a tile) keeps its own running
-// max / max / sum per column in shared memory, [column slot][3][kEpilogueWarps * 32] doubles, folded once per kernel.
+// max / sum per column in shared memory, [column slot][2][kEpilogueWarps * 32] doubles, folded once per kernel.
 constexpr int kStatThreads = kEpilogueWarps * 32;
 // Pair modes.  The operand image is the dominant L2 -> SM traffic (every m-tile re-reads all of it); processing two
 // m-tiles against one staged chunk halves it.  M: missing data, issuer i runs plane i of both tiles (4 accumulators of
@@ -209,7 +209,7 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
   // running column statistics (kOutFusedStats): this thread's own accumulators, no atomics, fixed order
   double* my_stats = stats_acc + (warp - kEpilogueWarp0) * 32 + lane;
   if (OUT == kOutFusedStats) {
-    for (int i = 0; i < p.stats_cols * 3; ++i) my_stats[i * kStatThreads] = 0.0;
+    for (int i = 0; i < p.stats_cols * 2; ++i) my_stats[i * kStatThreads] = 0.0;
   }
   uint32_t tile_no = 0;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
@@ -279,9 +279,10 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
         }
         const int k_hi = min(8, K - g * 8);
         if (OUT == kOutFusedStats) {
-          // what colstats_partial_kernel computes for the next A.dot: max |y| d, max |y| d mu, sum w y
-          const double abs_scale = fabs(row_scale), abs_a = fabs(row_a);
-          double* acc = my_stats + (size_t)(((g - g_first) / kSplit) * 8 * 3) * kStatThreads;
+          // what colstats_partial_kernel computes for the next A.dot: max(|y| d, |y| d mu) -- only the larger of its two
+          // maxima sets the fixed-point scale, and |y| d max(1, mu) is bit for bit that larger one -- and sum w y
+          const double abs_scale = fabs(row_scale), abs_a1 = fmax(fabs(row_a), 1.0);
+          double* acc = my_stats + (size_t)(((g - g_first) / kSplit) * 8 * 2) * kStatThreads;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             if (kk < k_hi) {
@@ -296,13 +297,12 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
               } else {
                 fdst[k] = y;
               }
-              double* a = acc + kk * 3 * kStatThreads;
+              double* a = acc + kk * 2 * kStatThreads;
               double v1 = fabs(y) * abs_scale;
               if (v1 != v1) v1 = INFINITY;   // NaN poisons the scale, as in the stand-alone pass
-              const double v2 = v1 * abs_a;
+              v1 *= abs_a1;
               if (v1 > a[0]) a[0] = v1;
-              if (v2 > a[kStatThreads]) a[kStatThreads] = v2;
-              a[2 * kStatThreads] = fma(row_shift, y, a[2 * kStatThreads]);
+              a[kStatThreads] = fma(row_shift, y, a[kStatThreads]);
             }
           }
         } else {
@@ -349,16 +349,15 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
     const int k = (warp - kEpilogueWarp0) * 32 + lane;
     if (k < K) {
       const int g = k >> 3;
-      const double* base = stats_acc + (size_t)(((g / kSplit) * 8 + (k & 7)) * 3) * kStatThreads + (g % kSplit) * 128;
-      double m1 = 0.0, m2 = 0.0, ws = 0.0;
+      const double* base = stats_acc + (size_t)(((g / kSplit) * 8 + (k & 7)) * 2) * kStatThreads + (g % kSplit) * 128;
+      double m1 = 0.0, ws = 0.0;
       for (int r = 0; r < 128; ++r) {
         m1 = fmax(m1, base[r]);
-        m2 = fmax(m2, base[kStatThreads + r]);
-        ws += base[2 * kStatThreads + r];
+        ws += base[kStatThreads + r];
       }
       double* out = p.fz.stats_partial + (size_t)blockIdx.x * 3 * K;
-      out[k] = m1;
-      out[K + k] = m2;
+      out[k] = m1;        // the larger of the two maxima of the stand-alone pass
+      out[K + k] = 0.0;
       out[2 * K + k] = ws;
     }
     // the last CTA to get here folds all partial rows (block order) into the final statistics

@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(256) colstats_partial_kernel(const TB* __restr
     out[2 * K + k] = ws;
   }
 }
-// stats layout: [0,K) mult, [K,2K) 1/mult, [2K,3K) shift = shift_sign * wsum, [3K,4K) amax, [4K,5K) amax2
+// stats layout: [0,K) mult, [K,2K) 1/mult, [2K,3K) shift = shift_sign * wsum, [3K,4K) amax, [4K,5K) amax2 (informative:
+// only max(amax, amax2) enters mult; the fused producers report that maximum as amax and 0 as amax2)
 // 1024 threads: thread (slice, k) folds blocks slice, slice+S, ... ; thread k then folds the slices in order.
 __global__ void __launch_bounds__(1024) colstats_finish_kernel(const double* __restrict__ partial, int n_blocks, int K,
                                                                double lim, double shift_sign,
@@ -1351,7 +1352,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
   if (stats_emitted) *stats_emitted = p.fuse == 2;
   const size_t stage_bytes = (size_t)8 * N * 32 * p.n_img;
   const size_t budget = 222 * 1024;  // 227 KB per CTA minus the static barriers / column constants (3 KB) and slack
-  // statistics accumulators of the epilogue threads (fuse == 2): [column slot][3][256] doubles behind the rings
+  // statistics accumulators of the epilogue threads (fuse == 2): [column slot][2][256] doubles behind the rings
   size_t scratch = 0;
   if (p.fuse == 2) {
     const int split = kEpilogueWarps / 4;
@@ -1361,7 +1362,9 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
       if (hi > cols) cols = hi;
     }
     p.stats_cols = cols;
-    scratch = (size_t)cols * 3 * kEpilogueWarps * 32 * sizeof(double);
+    scratch = (size_t)cols * 2 * kEpilogueWarps * 32 * sizeof(double);
+    const size_t fold = (size_t)3 * kEpilogueWarps * 32 * sizeof(double);   // the last CTA's fold reuses it: [slices][3][K]
+    if (scratch < fold) scratch = fold;
     if (scratch + (size_t)kMaxTileStages * kTileBytes + 2 * stage_bytes > budget) {   // no room: stand-alone pass
       scratch = 0;
       p.fuse = 1;
