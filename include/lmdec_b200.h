@@ -139,8 +139,8 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
  * bit 4 (transpose = 1 only) = also leave in `work` the column statistics (fixed-point multiplier, rank-1 shift) of `out`
  * taken as the operand of the A.dot that follows in the power iteration (x = A (A^T q), iter_methods.py:383): the
  * tensor-core epilogue reduces them while it writes `out` and the last CTA folds them (K <= 32, unsplit contraction;
- * otherwise one extra pass over out; uses one device-wide ticket counter, so two such calls must not run concurrently
- * on different streams);  bit 5 = the column
+ * otherwise one extra pass over out; the last double of `work` is the ticket counter of that fold: zero-fill `work` once
+ * before the first call with this bit, every launch leaves it zero);  bit 5 = the column
  * statistics of B are already in `work` -- left there by the previous A^T product with bit 4 (transpose = 0: B is all
  * m_limit rows of that `out`, unmodified) or by lmdec_cholqr2_small (transpose = 1: B is its Q) -- and the pass over B
  * for them is skipped.

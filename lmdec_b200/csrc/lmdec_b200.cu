@@ -34,7 +34,6 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_mma_events;
 static bool g_mma_timing = false;
 static int g_sm_reserve = 0;
 static int g_pair_min_chunks = 64;
-__device__ unsigned int g_stats_ticket = 0;   // geno_mma's last-CTA fold of the output statistics (zero between launches)
 static int g_issuer_groups = 2;   // single-tile work items: issuer pairs taking alternate chunks (1 = one pair)
 static int g_prod_groups2 = 1;
 static int g_pair_mode = 1;   // lmdec_set_pair_mode: 0 disables the two-tiles-per-B-stage schedule (A/B tests)  // SMs left free for concurrently running collectives (row-sharded runs)
@@ -1474,7 +1473,9 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
   return check_launch("lmdec_sqdiff", 2);
 }
 
-int64_t lmdec_apply_work_doubles(int K) { return (int64_t)5 * K + (int64_t)kStatsMaxBlocks * 3 * K; }
+// [0, 5K) statistics | [5K, 5K + 592*3K) partial rows | one more double: the ticket counter of the epilogue's last-CTA
+// fold (flag 16), which must be zero before the first call and is left zero by every launch
+int64_t lmdec_apply_work_doubles(int K) { return (int64_t)5 * K + (int64_t)kStatsMaxBlocks * 3 * K + 1; }
 
 // column statistics of a float64 / float32 operand: partial rows, then the fold into stats (multiplier for `lim`, its
 // inverse, rank-1 shift, maxima)
@@ -1539,9 +1540,7 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
     if (rc) return rc;
   }
   // ---- tensor-core product, with the diagonal / rank-1 terms fused into its epilogue when it is not split
-  static thread_local unsigned int* ticket = nullptr;
-  if (emit_stats && !ticket && cudaGetSymbolAddress((void**)&ticket, g_stats_ticket) != cudaSuccess)
-    return fail("lmdec_operator_apply: cudaGetSymbolAddress");
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(work + lmdec_apply_work_doubles(K) - 1);
   // the following A.dot quantises `out` with has_missing ? 8P-3 : 8P-2 bits below its column maximum
   const double lim_next = ldexp(1.0, 8 * P - (has_missing ? 3 : 2));
   FusedFinalize fz;

@@ -329,7 +329,7 @@ class GenotypeOperator:
             nb_dot, nb_tdot = lib.lmdec_image_bytes(st.p, N), lib.lmdec_image_bytes(st.n, N)
             b = {
                 "N": N,
-                "work": torch.empty(lib.lmdec_apply_work_doubles(K), dtype=F64, device=dev),
+                "work": torch.zeros(lib.lmdec_apply_work_doubles(K), dtype=F64, device=dev),   # (ticket slot = 0)
                 "im1": torch.empty(max(nb_dot, nb_tdot), dtype=torch.int8, device=dev),
                 "im2": torch.empty(nb_dot, dtype=torch.int8, device=dev) if miss else None,
                 "acc0": torch.empty((max(st.n, st.p), K), dtype=torch.int64, device=dev),
