@@ -585,7 +585,10 @@ __global__ void __launch_bounds__(128) chol_whiten_kernel(const double* __restri
 
 // ---- single-launch CholeskyQR2 for small iterates (the n x K side of the power iteration)
 constexpr int kCqrThreads = 512;
-constexpr int kCqrCluster = 8;          // CTAs of one cluster share the row range; Gram partials meet through DSMEM
+#ifndef LMDEC_CQR_CLUSTER
+#define LMDEC_CQR_CLUSTER 8
+#endif
+constexpr int kCqrCluster = LMDEC_CQR_CLUSTER;   // CTAs of one cluster share the row range; Gram partials meet through DSMEM
 constexpr int kCqrSliceDoubles = 8192;  // per-CTA row slice kept in shared memory (x2: input and first-pass output)
 
 // Cholesky whitening of the K x K Gram matrix G (shared memory) by the whole block, one matrix element per thread
@@ -1656,6 +1659,7 @@ int lmdec_cholqr2_small(const double* X, int64_t ldx, int64_t n, int K, double r
   static thread_local bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(cholqr2_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    if (kCqrCluster > 8) cudaFuncSetAttribute(cholqr2_small_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     attr_set = true;
   }
   cholqr2_small_kernel<<<kCqrCluster, kCqrThreads, smem, (cudaStream_t)stream>>>(X, ldx, n, K, (int)per, rank_tol, Q,

@@ -233,8 +233,8 @@ def qr_pack(r1, r2, g2, f1, f2) -> torch.Tensor:
 
 
 def cholqr2_small_fits(n: int, K: int) -> bool:
-    per = -(-n // 8)
-    return K <= 32 and per * K * 8 <= _capi.load().lmdec_cholqr2_small_max_elems()
+    ctas = _capi.load().lmdec_cholqr2_small_max_elems() // 8192      # CTAs of the cluster, 8192 doubles of slice each
+    return K <= 32 and ctas > 0 and -(-n // ctas) * K <= 8192
 
 
 def cholqr2_small(x: torch.Tensor, rank_tol: float = 1e-12, stats_work: torch.Tensor = None, stats_lim: float = 0.0):
