@@ -266,7 +266,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     time.sleep(0.05)
     store_mod.KERNEL_EVENTS = []
-    lib.lmdec_kernel_timing(1)
+    store.ctx.timing(True)
     launches0 = lib.lmdec_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -288,11 +288,8 @@ def run_ours(args):
     k_ms = {"dot": [], "tdot": []}          # whole operator application (stats + planes + product + finalize)
     for tag, a, b in kernel_events:
         k_ms[tag].append(a.elapsed_time(b))
-    import ctypes
-    mma_total_ms, mma_launches = ctypes.c_double(0), ctypes.c_int64(0)
-    lib.lmdec_kernel_timing_read(ctypes.byref(mma_total_ms), ctypes.byref(mma_launches))
-    lib.lmdec_kernel_timing(0)
-    mma_total_ms, mma_launches = mma_total_ms.value, mma_launches.value
+    mma_total_ms, mma_launches = store.ctx.timing_read()
+    store.ctx.timing(False)
 
     # ---- e2e: public operator API with host operands (pinned), H2D + D2H inside the timed region
     q_host = torch.from_numpy(np.linalg.qr(x0_full[my_rows])[0]).pin_memory()

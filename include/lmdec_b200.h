@@ -10,7 +10,9 @@
  *   - all pointers are DEVICE pointers unless the name ends in _host; the caller (Python/PyTorch) owns all memory;
  *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it;
  *   - return value 0 = ok, nonzero = error; lmdec_last_error() returns a message for the calling thread;
- *   - no global state: thread-compatible (one stream per caller).
+ *   - no mutable global state: tunables and the kernel-timing events live in an opaque lmdec_ctx the caller owns
+ *     (one per thread / stream; NULL = defaults); the only process-wide objects are the thread-local error string and
+ *     an atomic launch counter.  Thread-compatible.
  *
  * Genotype store ("tile store"): 2-bit dosage codes, 4 per byte, LSB first: 0,1,2 = dosage, 3 = missing (NaN).
  * A PLINK .bed 2-bit field (hi lo): 00 hom-A1, 01 missing, 10 het, 11 hom-A2 (pandas_plink reads these as 0, NaN, 1, 2)
@@ -37,6 +39,25 @@ enum lmdec_dtype { LMDEC_I8 = 0, LMDEC_U8 = 1, LMDEC_F32 = 2, LMDEC_F64 = 3 };
 
 const char* lmdec_last_error(void);
 int lmdec_abi_version(void);
+/* content hash of the CUDA sources this binary was built from (the Python loader rebuilds a stale library) */
+const char* lmdec_source_hash(void);
+
+/* Caller-owned context for the product kernel: tunables (below) and CUDA-event timing of its launches. */
+typedef struct lmdec_ctx lmdec_ctx;
+lmdec_ctx* lmdec_ctx_create(void);
+void lmdec_ctx_destroy(lmdec_ctx* ctx);
+enum lmdec_knob {
+  LMDEC_KNOB_SM_RESERVE = 0,      /* SMs left out of the persistent grid so a collective on another stream can run; 0 */
+  LMDEC_KNOB_PAIR_MODE = 1,       /* 1: long contractions process two 128-row tiles per staged operand chunk; 0: one */
+  LMDEC_KNOB_PAIR_MIN_CHUNKS = 2, /* shortest contraction, in 256-wide chunks, that uses pair mode; 64 */
+  LMDEC_KNOB_ISSUER_GROUPS = 3,   /* 2: two MMA issuer pairs take alternate chunks of single-tile work items; 1: one */
+  LMDEC_KNOB_PRODUCER_GROUPS = 4  /* 2: two decode groups on alternate tile-chunks when no code is missing; 1: one */
+};
+int lmdec_ctx_set(lmdec_ctx* ctx, int knob, int value);
+int lmdec_ctx_get(const lmdec_ctx* ctx, int knob);
+/* CUDA-event timing of the product kernel's launches made through ctx, on their launching stream (bench.py's roofline) */
+void lmdec_ctx_timing(lmdec_ctx* ctx, int on);
+int lmdec_ctx_timing_read(lmdec_ctx* ctx, double* total_ms_host, int64_t* launches_host);
 /* number of CUDA kernels this library has launched in the process (bench.py reports the delta per timed region) */
 long long lmdec_launch_count(void);
 
@@ -96,9 +117,9 @@ int lmdec_colabsmax(const double* B, int64_t ldb, int64_t kd_limit, int K, const
  *   splits             split-K factor; 0 = choose; >1 accumulates with int64 atomics (outputs are zeroed here);
  *                      a split never spans more than 65,536 contraction elements (int32 accumulators)
  * out0/out1: int64 [m_limit, K] row-major.  */
-int lmdec_geno_matmul(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit, int has_missing,
-                      int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N, int64_t* out0,
-                      int64_t* out1, int splits, void* stream);
+int lmdec_geno_matmul(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
+                      int has_missing, int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N,
+                      int64_t* out0, int64_t* out1, int splits, void* stream);
 
 /* out[m,k] = (acc0[m,k] + rowa[m]*acc1[m,k]) * colscale[k] * rowscale[m] + rowshift[m]*colshift[k]
  * (any of acc1/rowa, rowscale, rowshift/colshift may be NULL).  The diag / rank-1 terms of the operator algebra:
@@ -147,7 +168,7 @@ int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, co
  * Steps: column statistics of B (max for the fixed-point scale, weighted column sum for the rank-1 term), plane
  * quantisation, lmdec_geno_matmul, lmdec_finalize.  */
 int64_t lmdec_apply_work_doubles(int K);
-int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
+int lmdec_operator_apply(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
                          int has_missing, int transpose_flags, const void* B, int64_t ldb, int K, int P,
                          const double* scale, const double* impute, const double* center_w, double* work,
                          int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, void* out, int64_t ldo,
@@ -182,19 +203,6 @@ int lmdec_cholqr2_grid(const double* X, int64_t ldx, int64_t n, int K, double ra
 /* packed[0..K*K) = r2 r1, then flag1, flag2, max|g2 - I|: what the host reads back from one CholeskyQR2. */
 int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const int* flag1, const int* flag2, int K,
                   double* packed, void* stream);
-
-/* Leave `n_sms` SMs out of the persistent product kernel's grid so that a collective (NCCL) launched on another stream
- * can run concurrently with it; 0 (default) = use every SM.  Process-wide setting. */
-void lmdec_set_sm_reserve(int n_sms);
-/* 1 (default): long contractions process two 128-row tiles per staged operand chunk; 0: one tile (A/B comparison). */
-void lmdec_set_pair_mode(int on);
-/* Tuning / A-B switch: 2 (default) = two MMA issuer pairs take alternate contraction chunks of single-tile work items,
- * 1 = one pair issues every chunk.  Results are identical (integer accumulation). */
-void lmdec_set_issuer_groups(int groups);
-
-/* CUDA-event timing of lmdec_geno_matmul's kernel on its launching stream (bench.py's roofline figure). */
-void lmdec_kernel_timing(int on);
-int lmdec_kernel_timing_read(double* total_ms_host, int64_t* launches_host);
 
 #ifdef __cplusplus
 }

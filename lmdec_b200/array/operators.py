@@ -193,12 +193,29 @@ def is_sparse(a) -> bool:
 
 
 def as_operator(data, device=None):
-    from ..store import GenotypeOperator, _Transposed
+    from ..store import GenotypeOperator, GenotypeStore, _Transposed
     from .chained import ChainedArray
     from .scaled_legacy import ScaledCenterArray
     from .stacked import StackedArray
-    if isinstance(data, (GenotypeOperator, _Transposed, StackedArray, ChainedArray, ScaledCenterArray, DenseOperator,
-                         SparseOperator)):
+    if isinstance(data, (StackedArray, ChainedArray)):
+        # the make_snp_array pattern spelled with the containers (lmdec/decomp/utils.py:278-289) goes to the 2-bit
+        # tile store and the tensor-core products; any other tree keeps the generic container algebra
+        if os.environ.get("LMDEC_RECOGNISE", "1") != "0":
+            cached = getattr(data, "_geno_op", False)
+            if cached is False:
+                from .recognize import genotype_operator_from_containers
+                cached = data._geno_op = genotype_operator_from_containers(data)
+            if cached is not None:
+                return cached
+        return data
+    if isinstance(data, GenotypeStore):
+        # raw genotypes (what load_plink_array returns): usable as they are when nothing is missing; with missing
+        # codes the reference's float matrix would carry NaN into the QR (tests/test_iter_methods.py:318-325)
+        if data.has_missing:
+            raise np.linalg.LinAlgError("SVD did not converge (the genotype store holds missing codes: wrap it with "
+                                        "make_snp_array to mean-impute them)")
+        return GenotypeOperator(data, None, None)
+    if isinstance(data, (GenotypeOperator, _Transposed, ScaledCenterArray, DenseOperator, SparseOperator)):
         return data
     if is_sparse(data):
         return SparseOperator(data, device=device)

@@ -30,13 +30,18 @@ int check_launch(const char* what, int n_kernels = 1) {
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 }  // namespace
 
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_mma_events;
-static bool g_mma_timing = false;
-static int g_sm_reserve = 0;
-static int g_pair_min_chunks = 64;
-static int g_issuer_groups = 2;   // single-tile work items: issuer pairs taking alternate chunks (1 = one pair)
-static int g_prod_groups2 = 1;
-static int g_pair_mode = 1;   // lmdec_set_pair_mode: 0 disables the two-tiles-per-B-stage schedule (A/B tests)  // SMs left free for concurrently running collectives (row-sharded runs)
+// Per-caller context (include/lmdec_b200.h): every tunable and the kernel-timing events live here, not in globals.
+struct lmdec_ctx {
+  int n_sm = 0;
+  int sm_reserve = 0;        // SMs left free for concurrently running collectives (row-sharded runs)
+  int pair_mode = 1;         // 0 disables the two-tiles-per-B-stage schedule (A/B tests)
+  int pair_min_chunks = 64;  // shortest contraction (256-wide chunks) that pairs
+  int issuer_groups = 2;     // single-tile work items: issuer pairs taking alternate chunks (1 = one pair)
+  int producer_groups = 2;   // 2: two producer groups on alternate tile-chunks when there is no missing data
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+};
+static const lmdec_ctx kDefaultCtx{};
 
 namespace lmdec {
 
@@ -1146,7 +1151,12 @@ using namespace lmdec;
 extern "C" {
 
 const char* lmdec_last_error(void) { return g_err; }
-int lmdec_abi_version(void) { return 1; }
+int lmdec_abi_version(void) { return 2; }
+#ifndef LMDEC_SRC_HASH
+#define LMDEC_SRC_HASH "unknown"
+#endif
+static const char kSrcHashMarker[] = "LMDEC_SRC_HASH=" LMDEC_SRC_HASH;   // also found by scanning the file (_build.py)
+const char* lmdec_source_hash(void) { return kSrcHashMarker + 15; }
 long long lmdec_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int64_t lmdec_store_bytes(int64_t M, int64_t Kd) { return cdiv(M, 128) * cdiv(Kd, 256) * 8192; }
@@ -1260,7 +1270,7 @@ int lmdec_colabsmax(const double* B, int64_t ldb, int64_t kd_limit, int K, const
 }  // extern "C"
 
 // fz (optional): finalize fused into the epilogue when the product is not split; *fused reports whether it was
-static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
+static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
                            int has_missing, int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N,
                            int64_t* out0, int64_t* out1, int splits, void* stream, const FusedFinalize* fz,
                            bool* fused, bool* stats_emitted = nullptr) {
@@ -1268,12 +1278,14 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
   if (m_limit <= 0 || m_limit > M || kd_limit <= 0 || kd_limit > Kd) return fail("lmdec_geno_matmul: bad limits");
   if (mode == 1 && (!has_missing || !out1)) return fail("lmdec_geno_matmul: mode 1 needs has_missing and out1");
   if (!image1 || !out0) return fail("lmdec_geno_matmul: null operand");
-  static thread_local int n_sm = 0;
+  const lmdec_ctx& ctx = ctx_in ? *ctx_in : kDefaultCtx;
   static thread_local bool attr_set = false;
+  int n_sm = ctx.n_sm;
   if (!n_sm) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (ctx_in) ctx_in->n_sm = n_sm;
   }
   GenoMmaParams p;
   memset(&p, 0, sizeof(p));
@@ -1295,13 +1307,13 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
   // pair mode: two m-tiles share every staged chunk of the operand image (halves the dominant L2 -> SM traffic).  Only
   // for long contractions (the accumulators are not double-buffered across work items) and when TMEM has room.
   p.pair = kPairNone;
-  if (p.m_tiles >= 2 && p.n_chunks >= g_pair_min_chunks && g_pair_mode) {
+  if (p.m_tiles >= 2 && p.n_chunks >= ctx.pair_min_chunks && ctx.pair_mode) {
     if (has_missing && N <= 64) p.pair = kPairM;
     else if (!has_missing && N <= 64) p.pair = kPairE;
     else if (!has_missing) p.pair = kPairT;
   }
   p.m_units = p.pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
-  p.issuer_groups = g_issuer_groups;
+  p.issuer_groups = ctx.issuer_groups;
   // TMEM budget (512 columns): accumulators first, the rest is the decoded-A ring.  Short contractions alternate two
   // accumulator sets so the epilogue overlaps the next tile; long ones (epilogue negligible) give the columns to a
   // deeper A ring instead.
@@ -1312,7 +1324,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
       p.acc_sets = 1;
       acc_cols = (p.pair == kPairT ? 2 : 4) * acc_w;
     } else {
-      p.acc_sets = (N <= 64 && p.n_chunks < g_pair_min_chunks) ? 2 : 1;
+      p.acc_sets = (N <= 64 && p.n_chunks < ctx.pair_min_chunks) ? 2 : 1;
       acc_cols = p.acc_sets * 2 * acc_w;
     }
     p.a_ring_col0 = acc_cols;
@@ -1327,7 +1339,7 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
     const int max_s = p.n_chunks / 4 > 1 ? (p.n_chunks / 4 < 256 ? p.n_chunks / 4 : 256) : 1;
     long long best = -1;
     for (int s_ = min_splits > 1 ? min_splits : 1; s_ <= max_s; ++s_) {
-      const long long waves = cdiv((long long)p.m_units * s_, n_sm - g_sm_reserve > 8 ? n_sm - g_sm_reserve : 8);
+      const long long waves = cdiv((long long)p.m_units * s_, n_sm - ctx.sm_reserve > 8 ? n_sm - ctx.sm_reserve : 8);
       const long long cost = waves * ((p.pair ? 2 : 1) * cdiv(p.n_chunks, s_) + 6) + (s_ > 1 ? 2 : 0);
       if (best < 0 || cost < best) {
         best = cost;
@@ -1398,32 +1410,32 @@ static int launch_geno_mma(const uint8_t* store, int64_t M, int64_t Kd, int64_t 
     if (mode == 1) cudaMemsetAsync(out1, 0, (size_t)m_limit * K * 8, st);
   }
   const int n_work = p.m_units * p.splits;
-  const int sm_avail = n_sm - g_sm_reserve > 8 ? n_sm - g_sm_reserve : 8;
+  const int sm_avail = n_sm - ctx.sm_reserve > 8 ? n_sm - ctx.sm_reserve : 8;
   const int grid = n_work < sm_avail ? n_work : sm_avail;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (g_mma_timing) {
+  if (ctx.timing) {
     cudaEventCreate(&ev0);
     cudaEventCreate(&ev1);
     cudaEventRecord(ev0, st);
   }
   // producer grouping (see geno_mma.cuh): two groups without missing data, one with
-  if (!has_missing && g_prod_groups2)
+  if (!has_missing && ctx.producer_groups == 2)
     geno_mma_kernel<2><<<grid, kThreads, smem, st>>>(p);
   else
     geno_mma_kernel<1><<<grid, kThreads, smem, st>>>(p);
-  if (g_mma_timing) {
+  if (ctx.timing) {
     cudaEventRecord(ev1, st);
-    g_mma_events.emplace_back(ev0, ev1);
+    ctx_in->events.emplace_back(ev0, ev1);
   }
   return check_launch("lmdec_geno_matmul");
 }
 
 extern "C" {
 
-int lmdec_geno_matmul(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit, int has_missing,
-                      int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N, int64_t* out0,
-                      int64_t* out1, int splits, void* stream) {
-  return launch_geno_mma(store, M, Kd, m_limit, kd_limit, has_missing, mode, image1, image2, K, P, N, out0, out1,
+int lmdec_geno_matmul(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
+                      int has_missing, int mode, const int8_t* image1, const int8_t* image2, int K, int P, int N,
+                      int64_t* out0, int64_t* out1, int splits, void* stream) {
+  return launch_geno_mma(ctx, store, M, Kd, m_limit, kd_limit, has_missing, mode, image1, image2, K, P, N, out0, out1,
                          splits, stream, nullptr, nullptr);
 }
 
@@ -1501,8 +1513,8 @@ static int launch_colstats(const void* B, bool b_f32, int64_t ldb, int64_t kd_li
   return check_launch("lmdec_operator_apply (colstats)", 2);
 }
 
-int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
-                         int has_missing, int transpose_flags, const void* B, int64_t ldb, int K, int P,
+int lmdec_operator_apply(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit,
+                         int64_t kd_limit, int has_missing, int transpose_flags, const void* B, int64_t ldb, int K, int P,
                          const double* scale, const double* impute, const double* center_w, double* work,
                          int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, void* out, int64_t ldo,
                          void* stream) {
@@ -1560,7 +1572,7 @@ int lmdec_operator_apply(const uint8_t* store, int64_t M, int64_t Kd, int64_t m_
   fz.stats_lim = lim_next;
   fz.stats_ticket = ticket;
   bool fused = false, emitted = false;
-  rc = launch_geno_mma(store, M, Kd, m_limit, kd_limit, has_missing, (transpose && has_missing) ? 1 : 0, image1,
+  rc = launch_geno_mma(ctx, store, M, Kd, m_limit, kd_limit, has_missing, (transpose && has_missing) ? 1 : 0, image1,
                        two ? image2 : nullptr, K, P, N, acc0, (transpose && has_missing) ? acc1 : nullptr, 0, stream,
                        &fz, &fused, &emitted);
   if (rc) return rc;
@@ -1726,33 +1738,62 @@ int lmdec_trace_read(long long* host_out) {
 }
 #endif
 
-void lmdec_set_pair_mode(int on) {
-  g_pair_mode = on != 0;
-  if (on > 1) g_pair_min_chunks = on;  // values > 1 also set the shortest contraction (in 256-wide chunks) that pairs
-}
+lmdec_ctx* lmdec_ctx_create(void) { return new lmdec_ctx(); }
 
-void lmdec_set_issuer_groups(int groups) { g_issuer_groups = groups == 1 ? 1 : 2; }
-
-void lmdec_set_sm_reserve(int n_sms) { g_sm_reserve = n_sms < 0 ? 0 : n_sms; }
-
-void lmdec_kernel_timing(int on) {
-  for (auto& e : g_mma_events) {
+static void ctx_drop_events(lmdec_ctx* ctx) {
+  for (auto& e : ctx->events) {
     cudaEventDestroy(e.first);
     cudaEventDestroy(e.second);
   }
-  g_mma_events.clear();
-  g_mma_timing = on != 0;
+  ctx->events.clear();
 }
-int lmdec_kernel_timing_read(double* total_ms, int64_t* launches) {
+
+void lmdec_ctx_destroy(lmdec_ctx* ctx) {
+  if (!ctx) return;
+  ctx_drop_events(ctx);
+  delete ctx;
+}
+
+int lmdec_ctx_set(lmdec_ctx* ctx, int knob, int value) {
+  if (!ctx) return fail("lmdec_ctx_set: null context");
+  switch (knob) {
+    case LMDEC_KNOB_SM_RESERVE: ctx->sm_reserve = value < 0 ? 0 : value; return 0;
+    case LMDEC_KNOB_PAIR_MODE: ctx->pair_mode = value != 0; return 0;
+    case LMDEC_KNOB_PAIR_MIN_CHUNKS: ctx->pair_min_chunks = value < 2 ? 2 : value; return 0;
+    case LMDEC_KNOB_ISSUER_GROUPS: ctx->issuer_groups = value == 1 ? 1 : 2; return 0;
+    case LMDEC_KNOB_PRODUCER_GROUPS: ctx->producer_groups = value == 1 ? 1 : 2; return 0;
+  }
+  return fail("lmdec_ctx_set: unknown knob");
+}
+
+int lmdec_ctx_get(const lmdec_ctx* ctx, int knob) {
+  const lmdec_ctx& c = ctx ? *ctx : kDefaultCtx;
+  switch (knob) {
+    case LMDEC_KNOB_SM_RESERVE: return c.sm_reserve;
+    case LMDEC_KNOB_PAIR_MODE: return c.pair_mode;
+    case LMDEC_KNOB_PAIR_MIN_CHUNKS: return c.pair_min_chunks;
+    case LMDEC_KNOB_ISSUER_GROUPS: return c.issuer_groups;
+    case LMDEC_KNOB_PRODUCER_GROUPS: return c.producer_groups;
+  }
+  return -1;
+}
+
+void lmdec_ctx_timing(lmdec_ctx* ctx, int on) {
+  if (!ctx) return;
+  ctx_drop_events(ctx);
+  ctx->timing = on != 0;
+}
+int lmdec_ctx_timing_read(lmdec_ctx* ctx, double* total_ms, int64_t* launches) {
+  if (!ctx) return fail("lmdec_ctx_timing_read: null context");
   double tot = 0;
-  for (auto& e : g_mma_events) {
+  for (auto& e : ctx->events) {
     cudaEventSynchronize(e.second);
     float ms = 0;
     cudaEventElapsedTime(&ms, e.first, e.second);
     tot += ms;
   }
   *total_ms = tot;
-  *launches = (int64_t)g_mma_events.size();
+  *launches = (int64_t)ctx->events.size();
   return 0;
 }
 

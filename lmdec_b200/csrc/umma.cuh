@@ -105,6 +105,23 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     if (++spins > LMDEC_MBAR_SPIN_LIMIT) __trap();
   }
 }
+// Waits that are off the critical path (epilogue warps waiting for a whole tile of MMAs, loaders waiting for a ring slot
+// several chunks ahead): sleep between polls, so that the polling loop does not take issue slots and ALU cycles from the
+// decode producers (in round 1 the polling loops were 20 % of all executed instructions, profiles/r02/).
+#ifndef LMDEC_PARK_NS
+#define LMDEC_PARK_NS 64
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed_a(uint32_t bar, uint32_t parity) {
+#if LMDEC_PARK_NS > 0
+  uint32_t spins = 0;
+  while (!mbar_try_wait_a(bar, parity)) {
+    __nanosleep(LMDEC_PARK_NS);
+    if (++spins > LMDEC_MBAR_SPIN_LIMIT) __trap();
+  }
+#else
+  mbar_wait_a(bar, parity);
+#endif
+}
 __device__ __forceinline__ void bulk_g2s_a(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
                "l"(gmem_src), "r"(bytes), "r"(bar)

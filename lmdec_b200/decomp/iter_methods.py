@@ -177,7 +177,67 @@ class PowerMethod(_IterAlgo):
         self._cache = {}
 
     def project(self, x, onto, scale_center_x: bool = True):
-        raise NotImplementedError  # as in the reference (iter_methods.py:348)
+        """Project new samples `x` [N, P] onto `onto` ([P, M], or [M, P] as the reference's docstring has it):
+        returns x' onto [N, M], where x' is `x` centred / scaled / mean-imputed with the moments of the matrix the last
+        ``svd`` ran on (``scale_center_x``), i.e. the principal-component scores of unseen samples.
+
+        The reference documents this method and then raises NotImplementedError (iter_methods.py:321-348); its xfail
+        test (tests/test_iter_methods.py:448-474) states the contract implemented here:
+        ``PM.project(y, onto=V_k.T) == ((y - mu) / std) @ V_k.T``.  A genotype `x` ({0,1,2,NaN}) is packed into a
+        2-bit store and the product is ONE ``lmdec_operator_apply`` with the stored moments (NaN -> the TRAINING mean of
+        the SNP, which centres to zero); any other `x` is a dense float64 product."""
+        from ..array.scaled_legacy import ScaledCenterArray
+        from ..store import GenotypeOperator, GenotypeStore, NotGenotypeError
+        if self.array is None:
+            raise ValueError("project needs the moments of a fitted matrix: call svd() first")
+        src = self.array
+        p_dim = tuple(x.shape)[1] if len(tuple(x.shape)) == 2 else None
+        if p_dim is None:
+            raise ValueError("expected a 2-D array of new samples, got shape {}".format(tuple(x.shape)))
+        onto_t = as_tensor(onto).to(F64)
+        if onto_t.ndim != 2 or p_dim not in tuple(onto_t.shape):
+            raise ValueError("P in shape of `x` {} and shape of `onto` {} must match".format(tuple(x.shape),
+                                                                                           tuple(onto_t.shape)))
+        if onto_t.shape[0] != p_dim:
+            onto_t = onto_t.T
+        onto_t = onto_t.contiguous()
+        mean = inv_std = impute = None
+        if isinstance(src, GenotypeOperator):
+            impute = src.impute_mean if src.impute_mean is not None else src.store.moments()[0]
+            if scale_center_x:
+                mean, inv_std = src.mean, src.inv_std
+        elif isinstance(src, ScaledCenterArray) and scale_center_x:
+            mean = src.center_vector.t if src.center else None
+            inv_std = src.scale_vector.t if src.scale else None
+        for v in (mean, inv_std):
+            if v is not None and v.shape[0] != p_dim:
+                raise ValueError("x has {} columns, the fitted moments {}".format(p_dim, v.shape[0]))
+        if isinstance(x, GenotypeOperator):
+            x = x.store
+        store = None
+        if isinstance(x, GenotypeStore):
+            store = x
+        elif getattr(src, "store", None) is not None or isinstance(src, ScaledCenterArray):
+            try:
+                store = GenotypeStore.from_dense(x)
+            except NotGenotypeError:
+                store = None
+        if store is not None:
+            op = GenotypeOperator(store, mean, inv_std, planes=getattr(src, "planes", 3))
+            if op.has_missing:
+                if impute is None:
+                    impute = mean if mean is not None else store.moments()[0]
+                op.impute_mean = impute.contiguous()
+            return DeviceArray(op.dot_t(onto_t))
+        xt = as_tensor(x).to(F64)
+        if bool(torch.isnan(xt).any().item()):
+            fill = impute if impute is not None else (mean if mean is not None else torch.nanmean(xt, dim=0))
+            xt = torch.where(torch.isnan(xt), fill.expand_as(xt), xt)
+        if mean is not None:
+            xt = xt - mean
+        if inv_std is not None:
+            xt = xt * inv_std
+        return DeviceArray(xt @ onto_t)
 
     # ------------------------------------------------------------------ per-iterate products
     def _state(self, x: torch.Tensor) -> dict:
@@ -228,13 +288,24 @@ class PowerMethod(_IterAlgo):
     def _noise(self, x: torch.Tensor, lmbd, seed=None, sharded: bool = True) -> torch.Tensor:
         """x <- (1-lmbd) x + lmbd ||x_col|| / sqrt(n) N(0,1)   (iter_methods.py:372-375, 577-580)."""
         gen = torch.Generator(device=x.device)
+        # x is REPLICATED over the ranks that shard the other axis (the n x K iterate over SNP shards; the p x K
+        # hand-over of the batched method over sample-row shards): every rank must then draw the same noise, or the
+        # ranks leave the loop at different iterations and the next collective hangs.  An unseeded draw is agreed
+        # on through one 8-byte all-reduce.
+        replicated_over = _snp_group_of(self.array) if sharded else _group_of(self.array)
         if seed is None:
-            gen.seed()
+            if replicated_over is not None:
+                import torch.distributed as dist
+                s_ = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(x.device)
+                dist.all_reduce(s_, op=dist.ReduceOp.MAX, group=replicated_over)
+                gen.manual_seed(int(s_.item()))
+            else:
+                gen.seed()
         else:
             gen.manual_seed(int(seed))
         c2 = (x * x).sum(dim=0)
-        g = _group_of(self.array) if sharded else None
-        n = self.array.shape[0] if sharded else x.shape[0]
+        g = _group_of(self.array) if sharded else _snp_group_of(self.array)
+        n = self.array.shape[0] if sharded else self.array.shape[1]
         if g is not None:
             import torch.distributed as dist
             dist.all_reduce(c2, group=g)

@@ -7,7 +7,7 @@ from typing import Optional
 import torch
 
 from ..device import DeviceArray, as_tensor
-from ..store import GenotypeOperator, GenotypeStore
+from ..store import GenotypeOperator, GenotypeStore, NotGenotypeError
 
 PowerMethodSummary = namedtuple("PowerMethodSummary", ["time", "acc", "iter"])
 
@@ -105,9 +105,12 @@ def make_snp_array(array, mean: bool = True, std: bool = True, std_method: str =
             store = GenotypeStore.from_dense(array, device=device, group=group, n_global=n_global,
                                              row_offset=row_offset, snp_group=snp_group, p_global=p_global,
                                              col_offset=col_offset)
-        except ValueError:
+        except NotGenotypeError:
             # not a genotype matrix (the reference's own tests feed random floats, tests/test_iter_methods.py:12-33):
-            # same operator over a dense device matrix, products are library GEMMs
+            # same operator over a dense device matrix.  Only this error is caught: a bad shape or a bad sharding
+            # specification must surface, and the dense operator knows nothing about shards.
+            if group is not None or snp_group is not None:
+                raise
             return _make_dense_snp_array(array, mean, std, std_method, mask_nan)
     if store.has_missing and not mask_nan:
         raise ValueError("array holds NaN; the 2-bit store always mean-imputes them (mask_nan=True)")

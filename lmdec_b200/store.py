@@ -57,6 +57,10 @@ def _round16(x: int) -> int:
     return (x + 15) // 16 * 16
 
 
+class NotGenotypeError(ValueError):
+    """the matrix holds values other than 0, 1, 2 and NaN (it cannot live in the 2-bit store)"""
+
+
 class GenotypeStore:
     """n x p genotypes (rows = samples) as two 2-bit tile stores on one GPU.
 
@@ -75,6 +79,7 @@ class GenotypeStore:
         if group is not None and snp_group is not None:
             raise ValueError("shard either the samples (group) or the SNPs (snp_group), not both")
         self.lib = _capi.load()
+        self.ctx = _capi.Context()          # tunables + kernel timing of every product launched over this store
         self.device = device or require_cuda()
         self.n, self.p = int(n), int(p)
         self.group = group
@@ -138,26 +143,45 @@ class GenotypeStore:
         self._counts = None
 
     @classmethod
-    def from_bed_bytes(cls, bed, n_samples: int, n_variants: int, device=None):
+    def from_bed_bytes(cls, bed, n_samples: int, n_variants: int, device=None, variants_as_rows: bool = False):
         """PLINK .bed payload (variant-major, after the 3-byte magic) -> store, without a float round trip.
         Replaces pandas_plink.read_plink under load_plink_array (lmdec/array/io.py:16-73).  Code map (the one
-        pandas_plink uses): 00 -> 0, 01 -> missing, 10 -> 1, 11 -> 2."""
-        self = cls(n_samples, n_variants, device=device)
+        pandas_plink uses): 00 -> 0, 01 -> missing, 10 -> 1, 11 -> 2.  The store has samples as rows (n = n_samples,
+        p = n_variants) unless `variants_as_rows` (the orientation ``read_plink`` itself returns)."""
+        base = cls(n_variants, n_samples, device=device)          # rows = variants: the .bed orientation
         bed_t = bed if isinstance(bed, torch.Tensor) else torch.from_numpy(np.frombuffer(bed, dtype=np.uint8).copy())
-        bed_t = bed_t.to(self.device)
+        bed_t = bed_t.to(base.device).contiguous()
         if bed_t.numel() != n_variants * ((n_samples + 3) // 4):
             raise ValueError("bed payload size does not match n_variants x ceil(n_samples/4)")
         st = _capi.stream_ptr()
-        _capi.check(self.lib.lmdec_recode_bed(_capi.ptr(bed_t), n_variants, n_samples, _capi.ptr(self.v_store), st))
-        _capi.check(self.lib.lmdec_store_transpose(_capi.ptr(self.v_store), n_variants, n_samples,
-                                                   _capi.ptr(self.s_store), st))
-        self.finish()
+        _capi.check(base.lib.lmdec_recode_bed(_capi.ptr(bed_t), n_variants, n_samples, _capi.ptr(base.s_store), st))
+        base.derive_snp_major()
+        base.finish()
+        return base if variants_as_rows else base.transposed()
+
+    def derive_snp_major(self):
+        """column-major store (M = p) from the row-major one (M = n): lmdec_store_transpose, codes untouched"""
+        _capi.check(self.lib.lmdec_store_transpose(_capi.ptr(self.s_store), self.n, self.p, _capi.ptr(self.v_store),
+                                                   _capi.stream_ptr()), "store_transpose")
+        self._counts = None
         return self
+
+    def transposed(self) -> "GenotypeStore":
+        """the p x n matrix over the SAME two tile stores (they swap roles; nothing is copied)"""
+        if self.group is not None or self.snp_group is not None:
+            raise NotImplementedError("transposed() of a sharded store")
+        t = GenotypeStore.__new__(GenotypeStore)
+        t.__dict__.update(self.__dict__)
+        t.n, t.p, t.n_global, t.p_global = self.p, self.n, self.p, self.n
+        t.s_store, t.v_store = self.v_store, self.s_store
+        t._counts = None
+        t._bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return t
 
     # ------------------------------------------------------------------ persistence (reference array/io.py:129-273)
     def save(self, path: str):
-        """Write the packed store (both orientations + shape) so that packing / the NaN scan is not repeated.
-        Stands where save_array / load_array_from_disk store the operator's members as zarr trees."""
+        """Raw tile stores + shape (no moments): see ``lmdec_b200.array.io.save_array`` for the operator tree that also
+        persists mean, 1/std, the imputation vector and the integer code counts."""
         import os
         os.makedirs(path, exist_ok=True)
         torch.save({"n": self.n, "p": self.p, "n_global": self.n_global, "row_offset": self.row_offset,
@@ -182,7 +206,7 @@ class GenotypeStore:
     def finish(self):
         bad = int(self._bad.item())
         if bad:
-            raise ValueError("genotype matrix holds values other than 0, 1, 2 and NaN")
+            raise NotGenotypeError("genotype matrix holds values other than 0, 1, 2 and NaN")
         return self
 
     # ------------------------------------------------------------------ exact integer content
@@ -247,6 +271,11 @@ class GenotypeOperator:
         self.inv_std = inv_std      # scaling vector (None = no scaling)
         self.planes = int(planes)
         self.rows = store.n if rows is None else int(rows)   # local row prefix
+        # global number of rows of this (view of the) operator: identical on every rank by construction, never derived
+        # from rank-local quantities (a prefix view clamps differently on every rank of a row-sharded store)
+        self.global_rows = store.n_global if rows is None or store.group is None else None
+        if rows is not None and store.group is None:
+            self.global_rows = self.rows
         self.has_missing = store.has_missing
         if self.has_missing and not impute:
             raise ValueError("the store holds missing genotypes; they are always mean-imputed")
@@ -258,20 +287,15 @@ class GenotypeOperator:
     @property
     def shape(self):
         """global shape: samples over all row shards x SNPs over all SNP shards"""
-        n = self.rows if self.store.group is None else self._global_rows()
-        return (n, self.store.p_global)
+        if self.store.group is None:
+            return (self.rows, self.store.p_global)
+        if self.global_rows is None:
+            raise ValueError("row-sharded operator built with an explicit local prefix: set `global_rows`")
+        return (self.global_rows, self.store.p_global)
 
     @property
     def local_cols(self):
         return self.store.p
-
-    def _global_rows(self):
-        if self.rows == self.store.n:
-            return self.store.n_global
-        import torch.distributed as dist
-        t = torch.tensor([self.rows], dtype=torch.int64, device=self.store.device)
-        dist.all_reduce(t, group=self.store.group)
-        return int(t.item())
 
     @property
     def local_rows(self):
@@ -305,12 +329,13 @@ class GenotypeOperator:
         start, stop, step = r.indices(self.shape[0])
         if start != 0 or step != 1:
             raise NotImplementedError("only row prefixes [0:m, :] are views of the store")
+        global_stop = stop
         if self.store.group is not None:
             # block-contiguous shards: the global prefix [0, stop) is this rank's [0, clamp(stop - offset)]
             stop = min(max(stop - self.store.row_offset, 0), self.store.n)
         op = GenotypeOperator.__new__(GenotypeOperator)
         op.__dict__.update(self.__dict__)
-        op.rows, op._t, op._buf = stop, None, self._buf
+        op.rows, op._t, op._buf, op.global_rows = stop, None, self._buf, global_stop
         return op
 
     # ------------------------------------------------------------------ buffers
@@ -318,8 +343,8 @@ class GenotypeOperator:
         P = self.planes
         N = _round16(K * P)
         if N > 128:
-            raise ValueError(f"k + buffer = {K} with {P} planes needs N = {N} > 128 tensor-core columns; "
-                             "lower `planes` or k + buffer")
+            raise ValueError(f"{K} operand columns with {P} planes need N = {N} > 128 tensor-core columns: "
+                             "dot_t / tdot_t split wider operands into column blocks")
         key = (K, P)
         b = self._buf.get(key)
         if b is None:
@@ -337,6 +362,11 @@ class GenotypeOperator:
             }
             self._buf[key] = b
         return b
+
+    def _max_cols(self) -> int:
+        """operand columns one product launch takes: K * planes <= 128 tensor-core columns (N of the MMA); wider
+        operands (any k + buffer <= min(n, p) is legal in the reference, iter_methods.py:351-355) run as column blocks"""
+        return 128 // self.planes
 
     def _center_w(self):
         if self.mean is None:
@@ -386,7 +416,7 @@ class GenotypeOperator:
         store_ptr = C.c_void_p(store.data_ptr() + (m0 // 128) * ((Kd + 255) // 256) * 8192)
         with _timed("tdot" if transpose else "dot"):
             _capi.check(lib.lmdec_operator_apply(
-                store_ptr, M - m0, Kd, m1 - m0, kd_lim, int(miss), flags, _capi.ptr(b_in), b_in.stride(0),
+                st.ctx.handle, store_ptr, M - m0, Kd, m1 - m0, kd_lim, int(miss), flags, _capi.ptr(b_in), b_in.stride(0),
                 K, self.planes,
                 off(self.inv_std) if row_vec else _capi.ptr(self.inv_std),
                 (off(self.impute_mean) if row_vec else _capi.ptr(self.impute_mean)) if miss else None,
@@ -420,6 +450,11 @@ class GenotypeOperator:
             raise ValueError("shapes {} and {} not aligned".format(self.shape, tuple(t.shape)))
         if t.dtype not in (F64, torch.float32):
             t = t.to(F64)
+        kc = self._max_cols()
+        if t.shape[1] > kc:
+            # more operand columns than one tensor-core N tile holds (K * planes > 128): column blocks, one product each
+            x = torch.cat([self.dot_t(t[:, k0:k0 + kc].contiguous()) for k0 in range(0, t.shape[1], kc)], dim=1)
+            return x
         if t.stride(1) != 1 or t.stride(0) != t.shape[1]:
             t = t.contiguous()
         x = self._apply(t, False)
@@ -451,6 +486,10 @@ class GenotypeOperator:
             raise ValueError("shapes {} and {} not aligned".format(self.shape[::-1], tuple(y.shape)))
         if y.dtype not in (F64, torch.float32):
             y = y.to(F64)
+        kc = self._max_cols()
+        if y.shape[1] > kc:
+            return torch.cat([self.tdot_t(y[:, k0:k0 + kc].contiguous(), out_dtype)
+                              for k0 in range(0, y.shape[1], kc)], dim=1)
         if y.stride(1) != 1 or y.stride(0) != y.shape[1]:
             y = y.contiguous()
         if self.store.group is None:
@@ -474,14 +513,14 @@ class GenotypeOperator:
         bounds = [min(st.p, (n_tiles * i // parts) * 128) for i in range(parts)] + [st.p]
         pending = []
         if parts > 1:
-            st.lib.lmdec_set_sm_reserve(int(os.environ.get("LMDEC_SM_RESERVE", "16")))
+            st.ctx.set(_capi.KNOB_SM_RESERVE, int(os.environ.get("LMDEC_SM_RESERVE", "16")))
         for i in range(parts):
             m0, m1 = bounds[i], bounds[i + 1]
             if m1 <= m0:
                 continue
             self._apply(y, True, out=w, m_range=(m0, m1), reuse_operand=bool(pending))
             pending.append(dist.all_reduce(w[m0:m1], group=st.group, async_op=True))
-        st.lib.lmdec_set_sm_reserve(0)
+        st.ctx.set(_capi.KNOB_SM_RESERVE, 0)
         for work in pending:
             work.wait()
         return w

@@ -949,3 +949,16 @@ class ScaledCenterArray:  # scaled_legacy.py:168-612
         sub = base[item]
         new.fit(sub)
         return new
+
+
+# --------------------------------------------------------------------------------------------------------------
+# sym_mat_mult_start  (NOT in the reference checkout; named by the project brief -- parity unpinned)
+# --------------------------------------------------------------------------------------------------------------
+def sym_mat_mult_start(array, k, seed=42):
+    """x0 = A A^T omega for the Gaussian omega of rnormal_start: one application of the Gram operator
+    (ScaledCenterArray.sym_mat_mult, scaled_legacy.py:379-399, without the factor) to the reference's own random start
+    (init_methods.py:180-184).  The reference has no function of this name; this restates the definition DESIGN.md
+    gives so that the CUDA path has something to be checked against."""
+    a = as_operator(array)
+    omega = rnormal_start(a, k, seed=seed)
+    return np.asarray(a.dot(np.asarray(a.T.dot(omega))))

@@ -32,7 +32,9 @@ def step_rate(op, K, n, p, steps=10):
         pm._solution_accuracy(x)
         x = pm._solution_step(x)
     torch.cuda.synchronize()
-    lib.lmdec_kernel_timing(1)
+    ctx = op.store.ctx if hasattr(op, 'store') else None
+    if ctx is not None:
+        ctx.timing(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -42,8 +44,9 @@ def step_rate(op, K, n, p, steps=10):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     tot, cnt = ctypes.c_double(0), ctypes.c_int64(0)
-    lib.lmdec_kernel_timing_read(ctypes.byref(tot), ctypes.byref(cnt))
-    lib.lmdec_kernel_timing(0)
+    if ctx is not None:
+        tot.value, cnt.value = ctx.timing_read()
+        ctx.timing(False)
     out = {"ms_per_step": ms, "tflops_step": 4.0 * n * p * K / (ms * 1e-3) / 1e12}
     if cnt.value:
         k_ms = tot.value / cnt.value

@@ -89,6 +89,45 @@ def main():
                 print(f"[dist_gpu_check world={world}] {name} (sub_svd_start={bool(kw2.get('sub_svd_start'))}): "
                       f"{'ok' if good else 'FAIL'}")
                 ok = ok and bool(good)
+    # ---- SNP shards with the DEFAULT start (sub_svd_start + unseeded noise, lmbd > 0): the iterate is replicated, so
+    # every rank must draw the same noise (agreed seed) and leave the loop at the same iteration -- a hang here was
+    # ADVICE r1 (medium).  Results depend on the noise: loose check against the oracle's converged subspace.
+    ops = make_snp_array(g[:, c_lo:c_hi], snp_group=dist.group.WORLD, p_global=p, col_offset=c_lo)
+    pmn = PowerMethod(k=k, buffer=buffer, tol=1e-6, scoring_method="q-vals", max_iter=60)     # lmbd=.01, seed=None
+    Un, Sn, Vn = pmn.svd(ops, verbose=False)
+    iters = [None] * world
+    dist.all_gather_object(iters, (pmn.num_iter, float(np.asarray(Sn)[0])))
+    if rank == 0:
+        Ur, Sr, Vr = oracle.PowerMethod(k=k, buffer=buffer, tol=1e-9, lmbd=0, sub_svd_start=False, max_iter=200).svd(
+            oracle.make_snp_array(g), x0=x0)
+        checks = {"unseeded noise: ranks agree on iterations and S": len(set(iters)) == 1,
+                  "unseeded noise: S vs converged oracle": np.allclose(np.asarray(Sn), Sr, rtol=1e-3)}
+        for name, good in checks.items():
+            print(f"[dist_gpu_check world={world}] {name}: {'ok' if good else 'FAIL'}")
+            ok = ok and bool(good)
+
+    # ---- SuccessiveBatchedPowerMethod over sample-row shards: prefix views clamp differently on every rank, their
+    # global shape must not (rank-dependent collective in GenotypeOperator.shape); 'rmse' reads it.
+    from lmdec_b200 import SuccessiveBatchedPowerMethod
+    opr = make_snp_array(g[lo:hi], group=dist.group.WORLD, n_global=n, row_offset=lo)
+    view = opr[0:600, :]
+    shapes = [None] * world
+    dist.all_gather_object(shapes, tuple(view.shape))
+    kw_sb = dict(k=4, buffer=4, f=.25, lmbd=0, tol=[1e-6, 1e-12], scoring_method=["q-vals", "rmse"], max_sub_iter=30)
+    sb = SuccessiveBatchedPowerMethod(**kw_sb)
+    from lmdec_b200.array.random import array_constant_partition, cumulative_partition
+    parts0 = cumulative_partition(array_constant_partition((n, p), f=.25, min_size=8))[0]
+    x0s = np.random.default_rng(1).standard_normal((parts0.stop, 8))          # start on the first row batch
+    x0_local = x0s[min(lo, parts0.stop):min(hi, parts0.stop)]                 # this rank's rows of that batch
+    Ub, Sb, Vb = sb.svd(opr, x0=x0_local)
+    if rank == 0:
+        Ur, Sr, Vr = oracle.SuccessiveBatchedPowerMethod(**kw_sb).svd(oracle.make_snp_array(g), x0=x0s)
+        checks = {"row-shard prefix view: same global shape on every rank": len(set(shapes)) == 1 and shapes[0] == (600, p),
+                  "row-shard SBPM: S vs oracle": np.allclose(np.asarray(Sb), Sr, rtol=1e-4),
+                  "row-shard SBPM: V vs oracle": oracle.subspace_dist(np.asarray(Vb).T, Vr.T, Sr) <= 1e-4}
+        for name, good in checks.items():
+            print(f"[dist_gpu_check world={world}] {name}: {'ok' if good else 'FAIL'}")
+            ok = ok and bool(good)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

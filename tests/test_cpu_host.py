@@ -10,16 +10,17 @@ from helpers import ROOT, oracle
 
 
 def test_capi_exports_every_declared_symbol():
-    from lmdec_b200 import _capi
+    from lmdec_b200 import _build, _capi
     header = open(os.path.join(ROOT, "include", "lmdec_b200.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
-    declared = set(re.findall(r"\b(lmdec_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(lmdec_[a-z0-9_]+)\s*\(", header))   # (typedefs / enums have no parenthesis)
     assert len(declared) >= 15
     lib = _capi.load()
     assert set(_capi.SIGNATURES) == declared, set(_capi.SIGNATURES) ^ declared
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.lmdec_abi_version() == 1
+    assert lib.lmdec_abi_version() == _capi.ABI_VERSION
+    assert lib.lmdec_source_hash().decode() == _build.source_hash()      # the shipped binary is built from these sources
     # pure host helpers of the ABI (no device needed)
     assert lib.lmdec_store_bytes(1, 1) == 8192
     assert lib.lmdec_store_bytes(2504, 1_000_000) == 20 * 3907 * 8192

@@ -112,7 +112,7 @@ def test_geno_matmul_exact(cuda, M, Kd, K, P, miss, mode, splits):
     im1, im2 = _quantize(torch, capi, lib, Bd, Kd, K, P, N, multd, r1d, r2d if two_images else None)
     out0 = torch.full((M, K), -7, dtype=torch.int64, device=cuda)
     out1 = torch.full((M, K), -7, dtype=torch.int64, device=cuda)
-    capi.check(lib.lmdec_geno_matmul(capi.ptr(store), M, Kd, M, Kd, has_missing, mode, capi.ptr(im1), capi.ptr(im2),
+    capi.check(lib.lmdec_geno_matmul(None, capi.ptr(store), M, Kd, M, Kd, has_missing, mode, capi.ptr(im1), capi.ptr(im2),
                                      K, P, N, capi.ptr(out0), capi.ptr(out1), splits, capi.stream_ptr()), "matmul")
     torch.cuda.synchronize()
     q1 = np.rint((B * r1[:, None]) * mult).astype(np.int64)
@@ -144,7 +144,7 @@ def test_geno_matmul_prefix_limits(cuda):
         im1, _ = _quantize(torch, capi, lib, Bd, kd_lim, K, P, N, multd)
         out0 = torch.full((M, K), -7, dtype=torch.int64, device=cuda)
         out1 = torch.full((M, K), -7, dtype=torch.int64, device=cuda)
-        capi.check(lib.lmdec_geno_matmul(capi.ptr(store), M, Kd, m_lim, kd_lim, 1, 1, capi.ptr(im1), None, K, P, N,
+        capi.check(lib.lmdec_geno_matmul(None, capi.ptr(store), M, Kd, m_lim, kd_lim, 1, 1, capi.ptr(im1), None, K, P, N,
                                          capi.ptr(out0), capi.ptr(out1), 0, capi.stream_ptr()))
         q1 = np.rint(B[:kd_lim] * mult).astype(np.int64)
         sub = g[:m_lim, :kd_lim]

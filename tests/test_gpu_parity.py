@@ -365,13 +365,15 @@ def test_epilogue_column_statistics_match_standalone_pass(cuda, n, p, K, miss):
     assert "emitted" not in buf
     x_plain = op.dot_t(t.clone())                      # another tensor object: the stand-alone statistics pass runs
     stats_plain = buf["work"][:5 * K].cpu().numpy().copy()
-    assert np.array_equal(stats_fused[:2 * K], stats_plain[:2 * K])           # mult, 1/mult
-    assert np.array_equal(np.maximum(stats_fused[3 * K:4 * K], stats_fused[4 * K:]),
-                          np.maximum(stats_plain[3 * K:4 * K], stats_plain[4 * K:]))   # the maximum that sets the scale
+    # mult, 1/mult and the maximum that sets the scale: the float32 epilogue takes the maximum on the fp32 pipe (two
+    # roundings of 2^-24 against the float64 pass); the fixed-point range keeps a factor ~2 of headroom above `lim`
+    np.testing.assert_allclose(stats_fused[:2 * K], stats_plain[:2 * K], rtol=5e-7)
+    np.testing.assert_allclose(np.maximum(stats_fused[3 * K:4 * K], stats_fused[4 * K:]),
+                               np.maximum(stats_plain[3 * K:4 * K], stats_plain[4 * K:]), rtol=5e-7)
     bound = 2.0 * stats_plain[3 * K:].max() * p               # sum_r |w_r t_rk| <= p max|mu| max|d t|
     np.testing.assert_allclose(stats_fused[2 * K:3 * K], stats_plain[2 * K:3 * K], rtol=0, atol=1e-14 * bound)
     np.testing.assert_allclose(x_fused.cpu().numpy(), x_plain.cpu().numpy(), rtol=0,
-                               atol=1e-9 * np.abs(x_plain.cpu().numpy()).max())
+                               atol=2e-6 * np.abs(x_plain.cpu().numpy()).max())   # two fixed-point scales 1e-7 apart
     t2 = op.tdot_t(y)
     t2 += 1.0                                           # modified in place: the emitted statistics no longer apply
     x_mod = op.dot_t(t2)

@@ -38,3 +38,10 @@ print("median producer wait for A stage (tile arrived -> A free):", np.median(tr
 print("median issuer: full seen -> committed:", np.median(tr[5, 8:56] - tr[4, 8:56]), "; st complete -> issuer sees full:", np.median(tr[4, 8:56] - tr[3, 8:56]))
 print("median issuer: previous commit -> B full seen:", np.median(tr[6, 9:56] - tr[5, 8:55]), "; B full seen -> A full seen:", np.median(tr[4, 8:56] - tr[6, 8:56]))
 print("median issuer: commit -> B released:", np.median(tr[8, 8:55] - tr[5, 8:55]), "; B released -> next B full seen:", np.median(tr[6, 9:56] - tr[8, 8:55]))
+
+# per work item (tile): issuer 0 done issuing (row 7), epilogue sees the accumulators full (9), tile finalized (10)
+print("tile  issued(7)  acc_full_seen(9)  finalized(10)   epilogue cycles   tile period")
+for i in range(1, 6):
+    print(f"{i:4d} {tr[7, i] - t0:10d} {tr[9, i] - t0:12d} {tr[10, i] - t0:14d} {tr[10, i] - tr[9, i]:14d} {tr[10, i] - tr[10, i - 1]:14d}")
+print("median epilogue cycles per tile:", np.median(tr[10, 1:6] - tr[9, 1:6]), " median tile period:", np.median(np.diff(tr[10, 0:6])))
+print("tile loader: median cycles between copies issued:", np.median(np.diff(tr[11, 8:56])), " copy issued -> tile seen by producer 0:", np.median(tr[0, 8:56] - tr[11, 8:56]))
