@@ -51,7 +51,9 @@ enum lmdec_knob {
   LMDEC_KNOB_PAIR_MODE = 1,       /* 1: long contractions process two 128-row tiles per staged operand chunk; 0: one */
   LMDEC_KNOB_PAIR_MIN_CHUNKS = 2, /* shortest contraction, in 256-wide chunks, that uses pair mode; 64 */
   LMDEC_KNOB_ISSUER_GROUPS = 3,   /* 2: two MMA issuer pairs take alternate chunks of single-tile work items; 1: one */
-  LMDEC_KNOB_PRODUCER_GROUPS = 4  /* 2: two decode groups on alternate tile-chunks when no code is missing; 1: one */
+  LMDEC_KNOB_PRODUCER_GROUPS = 4, /* 2: two decode groups on alternate tile-chunks when no code is missing; 1: one */
+  LMDEC_KNOB_PRODUCER_GROUPS_MISSING = 5, /* the same when codes are missing (only with a decoded-operand ring >= 3 deep) */
+  LMDEC_KNOB_ACC_SETS = 6         /* accumulator sets of single-tile work items: 0 = choose, 1 (deeper operand ring), 2 */
 };
 int lmdec_ctx_set(lmdec_ctx* ctx, int knob, int value);
 int lmdec_ctx_get(const lmdec_ctx* ctx, int knob);

@@ -91,7 +91,8 @@ def load():
 
 
 # knobs of lmdec_ctx_set (include/lmdec_b200.h, enum lmdec_knob)
-KNOB_SM_RESERVE, KNOB_PAIR_MODE, KNOB_PAIR_MIN_CHUNKS, KNOB_ISSUER_GROUPS, KNOB_PRODUCER_GROUPS = range(5)
+(KNOB_SM_RESERVE, KNOB_PAIR_MODE, KNOB_PAIR_MIN_CHUNKS, KNOB_ISSUER_GROUPS, KNOB_PRODUCER_GROUPS,
+ KNOB_PRODUCER_GROUPS_MISSING, KNOB_ACC_SETS) = range(7)
 
 
 class Context:
@@ -106,8 +107,11 @@ class Context:
             self.set(KNOB_PAIR_MODE, v)
             if v > 1:
                 self.set(KNOB_PAIR_MIN_CHUNKS, v)
-        if os.environ.get("LMDEC_ISSUER_GROUPS"):
-            self.set(KNOB_ISSUER_GROUPS, int(os.environ["LMDEC_ISSUER_GROUPS"]))
+        for env, knob in (("LMDEC_ISSUER_GROUPS", KNOB_ISSUER_GROUPS), ("LMDEC_ACC_SETS", KNOB_ACC_SETS),
+                          ("LMDEC_PRODUCER_GROUPS_MISSING", KNOB_PRODUCER_GROUPS_MISSING),
+                          ("LMDEC_PRODUCER_GROUPS", KNOB_PRODUCER_GROUPS)):
+            if os.environ.get(env):
+                self.set(knob, int(os.environ[env]))
 
     def set(self, knob: int, value: int):
         check(self.lib.lmdec_ctx_set(self.handle, knob, int(value)), "lmdec_ctx_set")

@@ -134,6 +134,7 @@ struct GenoMmaParams {
   int m_units;             // work items per split: m_tiles, or ceil(m_tiles / 2) in pair mode
   int stats_off;           // byte offset of the statistics accumulators in dynamic shared memory (fuse == 2)
   int stats_cols;          // column slots per epilogue thread
+  int epi_staged;          // float32 output: the staged epilogue (epilogue_loop32) has its staging area at stats_off
   int issuer_groups;       // 2: chunk-interleaved issuer pairs (single-tile work items)
   int fuse;                // write the finalized float64 result from the epilogue (never with atomics)
   FusedFinalize fz;
@@ -494,8 +495,226 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
 }
 
 #ifndef LMDEC_EPI_F32
-#define LMDEC_EPI_F32 1
+#define LMDEC_EPI_F32 2   // 0: float64 finalize for every output; 1: round-2 interim fp32 epilogue; 2: staged fp32 epilogue
 #endif
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Epilogue of the float32-output products (the steady-state A^T q of the iteration), round 2.
+// Measured on the round-1 epilogue (profiles/r02/trace_round2.txt): 8,860 cycles per 128 x 20 tile -- it, not the MMAs
+// (5,120 cycles), set the tile period -- spent on 4-byte stores scattered over 128 rows and on per-thread
+// read-modify-write statistics in shared memory.  Now:
+//   main phase   TMEM -> registers -> float32 finalize -> the tile's [rows][K] float32 image in one of two shared-memory
+//                staging buffers; the accumulators go back to the issuers as soon as the last tcgen05.ld has landed;
+//   post phase   the staged tile is contiguous in global memory (128 x K floats): ONE bulk copy (TMA engine) stores it;
+//                the column statistics of the tile are reduced from shared memory into two registers per thread
+//                (lane = column, warp w takes rows w, w + 8, ...), folded once at the end of the kernel.
+// Staging area: y[2][128][K] f32 | row_sc[2][128] f32 | row_w[2][128] f64 | fold_mx[8][32] u32 | fold_sm[8][32] f64 |
+//               last-CTA fold scratch [3 * kStatThreads] f64
+__host__ __device__ constexpr size_t epi32_stage_bytes(int K) {
+  return (size_t)2 * 128 * K * 4 + 2 * 128 * 4 + 2 * 128 * 8 + 8 * 32 * 4 + 8 * 32 * 8 + 3 * (size_t)kStatThreads * 8;
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stats_last_cta_fold(const GenoMmaParams& p, int k, int K, double* scratch);
+
+template <int P, int MODE, bool kStats>
+__device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t tbase, uint32_t acc_full,
+                                                uint32_t acc_empty, int warp, int lane, int acc_sets, uint32_t acc_w,
+                                                const double* fz_col, uint8_t* stage) {
+  const float* fz_col32 = reinterpret_cast<const float*>(fz_col + 256);
+  const int K = p.K;
+  float* stage_y = reinterpret_cast<float*>(stage);
+  float* row_sc = reinterpret_cast<float*>(stage + (size_t)2 * 128 * K * 4);
+  double* row_w = reinterpret_cast<double*>(stage + (size_t)2 * 128 * K * 4 + 1024);
+  uint32_t* fold_mx = reinterpret_cast<uint32_t*>(stage + (size_t)2 * 128 * K * 4 + 3072);
+  double* fold_sm = reinterpret_cast<double*>(stage + (size_t)2 * 128 * K * 4 + 4096);
+  double* fold_scratch = fold_sm + 8 * 32;
+  const int ew = warp - kEpilogueWarp0;      // 0 .. kEpilogueWarps-1
+  const int et = ew * 32 + lane;             // 0 .. kStatThreads-1
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
+  const int n_groups = (K + 7) / 8;
+  constexpr int kSplit = kEpilogueWarps / 4;
+  const int g_first = ew / 4;
+  const int n_work = p.m_units * p.splits;
+  const int shift1 = p.has_missing ? kMissShift : kValueShift;
+  const int tiles_per_item = p.pair ? 2 : 1;
+  const bool bulk_ok = p.fz.ldo == K && (reinterpret_cast<uintptr_t>(p.fz.out) & 15) == 0;
+  uint32_t mx = 0u;      // running column statistics of this thread's (column, row class): max as float bits, sum
+  double sm = 0.0;
+  uint32_t tile_no = 0, ti = 0;
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
+    const int unit = w % p.m_units;
+    const uint32_t set = p.pair ? 0u : tile_no % acc_sets;
+    const uint32_t set_phase = p.pair ? (tile_no & 1) : ((tile_no / acc_sets) & 1);
+    mbar_wait_relaxed_a(acc_full + 8 * set, set_phase);
+    if (ew == 0 && lane == 0) LMDEC_STAMP(9, (int)tile_no);
+    tc_fence_after_sync();
+    for (int t = 0; t < tiles_per_item; ++t, ++ti) {
+      const int mt = p.pair ? 2 * unit + t : unit;
+      const uint32_t slot = p.pair ? (uint32_t)t : set;
+      const uint32_t acc0 = lane_addr + (p.pair == kPairT ? slot : slot * 2) * acc_w, acc1 = acc0 + acc_w;
+      const long long m0 = (long long)mt * 128;
+      const long long m = m0 + row;
+      const int live_rows = mt < p.m_tiles ? (int)min((long long)128, p.m_limit - m0) : 0;
+      const bool live = row < live_rows;
+      const uint32_t buf = ti & 1;
+      float* sy = stage_y + (size_t)buf * 128 * K;
+      double row_a = 0.0, row_scale = 1.0, row_shift = 1.0;
+      if (live) {
+        if (p.fz.rowa) row_a = __ldg(p.fz.rowa + m);
+        if (p.fz.rowscale) row_scale = __ldg(p.fz.rowscale + m);
+        if (p.fz.rowshift) row_shift = __ldg(p.fz.rowshift + m);
+      }
+      const float rs32 = (float)row_scale, rsh32 = (float)row_shift;
+      const float c0 = rs32 * (1.0f / (1 << kValueShift));   // the decode's byte scaling folded into the row factors
+      const float c1 = MODE == 1 ? (float)((row_a - 3.0) * row_scale) * (1.0f / (1 << kMissShift))
+                                 : rs32 / (float)(1 << shift1);
+      if (g_first == 0) {   // one warp per lane quarter publishes the per-row factors of the statistics
+        row_sc[buf * 128 + row] = live ? fabsf(rs32) * fmaxf(fabsf((float)row_a), 1.0f) : 0.0f;
+        row_w[buf * 128 + row] = live ? row_shift : 0.0;
+      }
+      if (g_first >= n_groups && t == tiles_per_item - 1) {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(acc_empty + 8 * set);
+      }
+      for (int g = g_first; g < n_groups; g += kSplit) {
+        uint32_t r0[8 * P], r1[8 * P];
+        const uint32_t col = (uint32_t)g * 8 * P;
+#pragma unroll
+        for (int i = 0; i < P; ++i) tmem_ld8p(acc0 + col + i * 8, r0 + 8 * i);
+        if (p.pair == kPairT) {
+#pragma unroll
+          for (int i = 0; i < 8 * P; ++i) r1[i] = 0;
+        } else {
+#pragma unroll
+          for (int i = 0; i < P; ++i) tmem_ld8p(acc1 + col + i * 8, r1 + 8 * i);
+        }
+        tmem_wait_ld();
+        if (g + kSplit >= n_groups && t == tiles_per_item - 1) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(acc_empty + 8 * set);
+        }
+#ifdef LMDEC_ABL_NOEPI
+        if (r0[0] != 0x12345678u || r1[5] != 0x9abcdef0u) continue;
+#endif
+        if (!live) continue;
+        const int k_hi = min(8, K - g * 8);
+        float* dst = sy + (size_t)row * K + g * 8;
+        float y[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const int k = g * 8 + kk;
+          const float v = fmaf(planes_to_float<P>(r1 + kk * P), c1, planes_to_float<P>(r0 + kk * P) * c0);
+          y[kk] = kk < k_hi ? fmaf(v, fz_col32[k], rsh32 * fz_col32[128 + k]) : 0.0f;
+        }
+        if ((K & 3) == 0) {      // rows are 16-byte aligned in the staging buffer: two 128-bit stores per group
+          if (k_hi > 0) *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+          if (k_hi > 4) *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            if (kk < k_hi) dst[kk] = y[kk];
+        }
+      }
+      // ---- post phase: staged tile -> global (one bulk copy), column statistics from the staged tile
+      const uint32_t bytes = (uint32_t)live_rows * K * 4;
+      const bool bulk = bulk_ok && (bytes & 15) == 0;
+      fence_proxy_async_smem();
+      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store that read the OTHER buffer
+      asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
+      if (live_rows > 0) {
+        float* gdst = (float*)p.fz.out + m0 * p.fz.ldo;
+        if (bulk) {
+          if (et == 0) bulk_s2g(gdst, smem_u32(sy), bytes);
+        } else {
+          for (int i = et; i < live_rows * K; i += kStatThreads) gdst[(long long)(i / K) * p.fz.ldo + i % K] = sy[i];
+        }
+        if (kStats && lane < K) {
+          const float* sc = row_sc + buf * 128;
+          const double* wv = row_w + buf * 128;
+          for (int r = ew; r < live_rows; r += kEpilogueWarps) {
+            const float yv = sy[r * K + lane];
+            mx = max(mx, __float_as_uint(fabsf(yv) * sc[r]));   // |y| d max(1, mu) >= 0; a NaN sorts above +inf
+            sm = fma(wv[r], (double)yv, sm);
+          }
+        }
+      }
+      if (ew == 0 && lane == 0) LMDEC_STAMP(10, (int)tile_no);
+    }
+  }
+  if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (kStats) {
+    fold_mx[ew * 32 + lane] = mx;
+    fold_sm[ew * 32 + lane] = sm;
+    asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
+    const int k = et;
+    if (k < K) {
+      uint32_t m = 0u;
+      double ws = 0.0;
+      for (int j = 0; j < kEpilogueWarps; ++j) {    // fixed order
+        m = max(m, fold_mx[j * 32 + k]);
+        ws += fold_sm[j * 32 + k];
+      }
+      double* out = p.fz.stats_partial + (size_t)blockIdx.x * 3 * K;
+      out[k] = m > 0x7f800000u ? (double)INFINITY : (double)__uint_as_float(m);
+      out[K + k] = 0.0;
+      out[2 * K + k] = ws;
+    }
+    stats_last_cta_fold(p, k, K, fold_scratch);
+  }
+}
+
+// the last CTA to get here folds all per-CTA partial rows (block order) into the final statistics
+__device__ __forceinline__ void stats_last_cta_fold(const GenoMmaParams& p, int k, int K, double* scratch) {
+  __threadfence();
+  asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
+  if (k == 0) scratch[0] = atomicAdd(p.fz.stats_ticket, 1u) == gridDim.x - 1 ? 1.0 : 0.0;
+  asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
+  if (scratch[0] != 0.0) {
+    __threadfence();
+    // thread (slice, column) folds the rows slice, slice + n_sl, ...; thread `column` then folds the slices in order
+    asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
+    const int n_sl = kStatThreads / K, kc = k % K, sl = k / K;
+    if (sl < n_sl) {
+      double m1 = 0.0, m2 = 0.0, ws = 0.0;
+      for (unsigned b = sl; b < gridDim.x; b += n_sl) {
+        const double* in = p.fz.stats_partial + (size_t)b * 3 * K;
+        m1 = fmax(m1, __ldcg(in + kc));
+        m2 = fmax(m2, __ldcg(in + K + kc));
+        ws += __ldcg(in + 2 * K + kc);
+      }
+      scratch[(sl * 3 + 0) * K + kc] = m1;
+      scratch[(sl * 3 + 1) * K + kc] = m2;
+      scratch[(sl * 3 + 2) * K + kc] = ws;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
+    if (k < K) {
+      double m1 = 0.0, m2 = 0.0, ws = 0.0;
+      for (int j = 0; j < n_sl; ++j) {
+        m1 = fmax(m1, scratch[(j * 3 + 0) * K + k]);
+        m2 = fmax(m2, scratch[(j * 3 + 1) * K + k]);
+        ws += scratch[(j * 3 + 2) * K + k];
+      }
+      const double s_ = fmax(m1, m2);
+      const double mult = s_ > 0.0 ? p.fz.stats_lim / s_ : 1.0;   // as colstats_finish_kernel
+      double* st = p.fz.stats_final;
+      st[k] = mult;
+      st[K + k] = 1.0 / mult;
+      st[2 * K + k] = -ws;
+      st[3 * K + k] = m1;
+      st[4 * K + k] = m2;
+    }
+    if (k == 0) *p.fz.stats_ticket = 0u;
+  }
+}
+
 template <int P>
 __device__ __forceinline__ void epilogue_dispatch(const GenoMmaParams& p, uint32_t tbase, uint32_t acc_full,
                                                   uint32_t acc_empty, int warp, int lane, int acc_sets, uint32_t acc_w,
@@ -503,6 +722,17 @@ __device__ __forceinline__ void epilogue_dispatch(const GenoMmaParams& p, uint32
 #define LMDEC_EPI(MODE, OUT) \
   epilogue_loop<P, MODE, OUT>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col, stats_acc)
   const bool f32 = LMDEC_EPI_F32 && p.fuse && p.fz.out_f32;
+  if (f32 && p.epi_staged) {
+    uint8_t* stage = reinterpret_cast<uint8_t*>(stats_acc);
+    if (p.mode == 1) {
+      if (p.fuse == 2) epilogue_loop32<P, 1, true>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col, stage);
+      else epilogue_loop32<P, 1, false>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col, stage);
+    } else {
+      if (p.fuse == 2) epilogue_loop32<P, 0, true>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col, stage);
+      else epilogue_loop32<P, 0, false>(p, tbase, acc_full, acc_empty, warp, lane, acc_sets, acc_w, fz_col, stage);
+    }
+    return;
+  }
   if (p.mode == 1) {
     if (p.fuse == 2 && f32) LMDEC_EPI(1, kOutFusedStats32);
     else if (p.fuse == 2) LMDEC_EPI(1, kOutFusedStats);

@@ -38,6 +38,8 @@ struct lmdec_ctx {
   int pair_min_chunks = 64;  // shortest contraction (256-wide chunks) that pairs
   int issuer_groups = 2;     // single-tile work items: issuer pairs taking alternate chunks (1 = one pair)
   int producer_groups = 2;   // 2: two producer groups on alternate tile-chunks when there is no missing data
+  int producer_groups_missing = 1;   // the same with missing data (needs a decoded-A ring of >= 3 stages to pay)
+  int acc_sets = 0;          // accumulator sets of single-tile work items: 0 = choose, 1, 2
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
 };
@@ -1325,6 +1327,7 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
       acc_cols = (p.pair == kPairT ? 2 : 4) * acc_w;
     } else {
       p.acc_sets = (N <= 64 && p.n_chunks < ctx.pair_min_chunks) ? 2 : 1;
+      if (ctx.acc_sets == 1 || (ctx.acc_sets == 2 && N <= 64)) p.acc_sets = ctx.acc_sets;
       acc_cols = p.acc_sets * 2 * acc_w;
     }
     p.a_ring_col0 = acc_cols;
@@ -1366,9 +1369,17 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
   if (stats_emitted) *stats_emitted = p.fuse == 2;
   const size_t stage_bytes = (size_t)8 * N * 32 * p.n_img;
   const size_t budget = 222 * 1024;  // 227 KB per CTA minus the static barriers / column constants (3 KB) and slack
-  // statistics accumulators of the epilogue threads (fuse == 2): [column slot][2][256] doubles behind the rings
+  // shared memory behind the rings: the float32 epilogue's staging area (two output tiles, per-row factors, fold
+  // scratch: epi32_stage_bytes), or -- float64 output with fused statistics -- the per-thread accumulators
+  // [column slot][2][256] doubles of the round-1 epilogue
   size_t scratch = 0;
-  if (p.fuse == 2) {
+  p.epi_staged = 0;
+  if (p.fuse && p.fz.out_f32 && LMDEC_EPI_F32 == 2) {
+    scratch = (epi32_stage_bytes(K) + 15) / 16 * 16;
+    if (scratch + (size_t)2 * kTileBytes + 2 * stage_bytes <= budget) p.epi_staged = 1;
+    else scratch = 0;
+  }
+  if (p.fuse == 2 && !p.epi_staged) {
     const int split = kEpilogueWarps / 4;
     int cols = 0;
     for (int g = 0; g * 8 < K; ++g) {
@@ -1419,7 +1430,7 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
     cudaEventRecord(ev0, st);
   }
   // producer grouping (see geno_mma.cuh): two groups without missing data, one with
-  if (!has_missing && ctx.producer_groups == 2)
+  if (has_missing ? (ctx.producer_groups_missing == 2 && p.a_stages >= 3) : ctx.producer_groups == 2)
     geno_mma_kernel<2><<<grid, kThreads, smem, st>>>(p);
   else
     geno_mma_kernel<1><<<grid, kThreads, smem, st>>>(p);
@@ -1762,6 +1773,8 @@ int lmdec_ctx_set(lmdec_ctx* ctx, int knob, int value) {
     case LMDEC_KNOB_PAIR_MIN_CHUNKS: ctx->pair_min_chunks = value < 2 ? 2 : value; return 0;
     case LMDEC_KNOB_ISSUER_GROUPS: ctx->issuer_groups = value == 1 ? 1 : 2; return 0;
     case LMDEC_KNOB_PRODUCER_GROUPS: ctx->producer_groups = value == 1 ? 1 : 2; return 0;
+    case LMDEC_KNOB_PRODUCER_GROUPS_MISSING: ctx->producer_groups_missing = value == 2 ? 2 : 1; return 0;
+    case LMDEC_KNOB_ACC_SETS: ctx->acc_sets = value == 1 || value == 2 ? value : 0; return 0;
   }
   return fail("lmdec_ctx_set: unknown knob");
 }
@@ -1774,6 +1787,8 @@ int lmdec_ctx_get(const lmdec_ctx* ctx, int knob) {
     case LMDEC_KNOB_PAIR_MIN_CHUNKS: return c.pair_min_chunks;
     case LMDEC_KNOB_ISSUER_GROUPS: return c.issuer_groups;
     case LMDEC_KNOB_PRODUCER_GROUPS: return c.producer_groups;
+    case LMDEC_KNOB_PRODUCER_GROUPS_MISSING: return c.producer_groups_missing;
+    case LMDEC_KNOB_ACC_SETS: return c.acc_sets;
   }
   return -1;
 }

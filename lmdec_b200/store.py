@@ -93,6 +93,13 @@ class GenotypeStore:
         self._bad = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._counts = None
 
+    ndim = 2
+
+    @property
+    def shape(self):
+        """global shape (samples over all row shards, SNPs over all SNP shards)"""
+        return (self.n_global, self.p_global)
+
     # ------------------------------------------------------------------ construction
     @classmethod
     def from_dense(cls, array, device=None, rows_per_block: int = 8192, group=None, n_global=None, row_offset=0,
