@@ -134,6 +134,7 @@ struct GenoMmaParams {
   int m_units;             // work items per split: m_tiles, or ceil(m_tiles / 2) in pair mode
   int stats_off;           // byte offset of the statistics accumulators in dynamic shared memory (fuse == 2)
   int stats_cols;          // column slots per epilogue thread
+  int b_resident;          // the whole operand image stays in shared memory (short, unsplit contractions): no B ring
   int epi_staged;          // float32 output: the staged epilogue (epilogue_loop32) has its staging area at stats_off
   int issuer_groups;       // 2: chunk-interleaved issuer pairs (single-tile work items)
   int fuse;                // write the finalized float64 result from the epilogue (never with atomics)
@@ -508,10 +509,15 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
 //   post phase   the staged tile is contiguous in global memory (128 x K floats): ONE bulk copy (TMA engine) stores it;
 //                the column statistics of the tile are reduced from shared memory into two registers per thread
 //                (lane = column, warp w takes rows w, w + 8, ...), folded once at the end of the kernel.
-// Staging area: y[2][128][K] f32 | row_sc[2][128] f32 | row_w[2][128] f64 | fold_mx[8][32] u32 | fold_sm[8][32] f64 |
-//               last-CTA fold scratch [3 * kStatThreads] f64
+// Staging area (ONE tile: the next tile's main phase starts a whole tile of MMAs later, so a second buffer would buy
+// nothing and shared memory is better spent on the operand image / the tile ring):
+//   y[128][K] f32 (at least 3 * kStatThreads f64: the last CTA's fold reuses it) | row_sc[128] f32 | row_w[128] f64 |
+//   fold_mx[8][32] u32 | fold_sm[8][32] f64
+__host__ __device__ constexpr size_t epi32_y_bytes(int K) {
+  return (size_t)128 * K * 4 > 3 * (size_t)kStatThreads * 8 ? (size_t)128 * K * 4 : 3 * (size_t)kStatThreads * 8;
+}
 __host__ __device__ constexpr size_t epi32_stage_bytes(int K) {
-  return (size_t)2 * 128 * K * 4 + 2 * 128 * 4 + 2 * 128 * 8 + 8 * 32 * 4 + 8 * 32 * 8 + 3 * (size_t)kStatThreads * 8;
+  return epi32_y_bytes(K) + 128 * 4 + 128 * 8 + 8 * 32 * 4 + 8 * 32 * 8;
 }
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, uint32_t smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes)
@@ -526,12 +532,12 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
                                                 const double* fz_col, uint8_t* stage) {
   const float* fz_col32 = reinterpret_cast<const float*>(fz_col + 256);
   const int K = p.K;
-  float* stage_y = reinterpret_cast<float*>(stage);
-  float* row_sc = reinterpret_cast<float*>(stage + (size_t)2 * 128 * K * 4);
-  double* row_w = reinterpret_cast<double*>(stage + (size_t)2 * 128 * K * 4 + 1024);
-  uint32_t* fold_mx = reinterpret_cast<uint32_t*>(stage + (size_t)2 * 128 * K * 4 + 3072);
-  double* fold_sm = reinterpret_cast<double*>(stage + (size_t)2 * 128 * K * 4 + 4096);
-  double* fold_scratch = fold_sm + 8 * 32;
+  float* sy = reinterpret_cast<float*>(stage);
+  float* row_sc = reinterpret_cast<float*>(stage + epi32_y_bytes(K));
+  double* row_w = reinterpret_cast<double*>(stage + epi32_y_bytes(K) + 512);
+  uint32_t* fold_mx = reinterpret_cast<uint32_t*>(stage + epi32_y_bytes(K) + 1536);
+  double* fold_sm = reinterpret_cast<double*>(stage + epi32_y_bytes(K) + 2560);
+  double* fold_scratch = reinterpret_cast<double*>(stage);   // (the staged tile is dead by then)
   const int ew = warp - kEpilogueWarp0;      // 0 .. kEpilogueWarps-1
   const int et = ew * 32 + lane;             // 0 .. kStatThreads-1
   const int q = warp & 3;
@@ -546,7 +552,7 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
   const bool bulk_ok = p.fz.ldo == K && (reinterpret_cast<uintptr_t>(p.fz.out) & 15) == 0;
   uint32_t mx = 0u;      // running column statistics of this thread's (column, row class): max as float bits, sum
   double sm = 0.0;
-  uint32_t tile_no = 0, ti = 0;
+  uint32_t tile_no = 0;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
     const int unit = w % p.m_units;
     const uint32_t set = p.pair ? 0u : tile_no % acc_sets;
@@ -554,7 +560,7 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
     mbar_wait_relaxed_a(acc_full + 8 * set, set_phase);
     if (ew == 0 && lane == 0) LMDEC_STAMP(9, (int)tile_no);
     tc_fence_after_sync();
-    for (int t = 0; t < tiles_per_item; ++t, ++ti) {
+    for (int t = 0; t < tiles_per_item; ++t) {
       const int mt = p.pair ? 2 * unit + t : unit;
       const uint32_t slot = p.pair ? (uint32_t)t : set;
       const uint32_t acc0 = lane_addr + (p.pair == kPairT ? slot : slot * 2) * acc_w, acc1 = acc0 + acc_w;
@@ -562,8 +568,6 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
       const long long m = m0 + row;
       const int live_rows = mt < p.m_tiles ? (int)min((long long)128, p.m_limit - m0) : 0;
       const bool live = row < live_rows;
-      const uint32_t buf = ti & 1;
-      float* sy = stage_y + (size_t)buf * 128 * K;
       double row_a = 0.0, row_scale = 1.0, row_shift = 1.0;
       if (live) {
         if (p.fz.rowa) row_a = __ldg(p.fz.rowa + m);
@@ -575,8 +579,8 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
       const float c1 = MODE == 1 ? (float)((row_a - 3.0) * row_scale) * (1.0f / (1 << kMissShift))
                                  : rs32 / (float)(1 << shift1);
       if (g_first == 0) {   // one warp per lane quarter publishes the per-row factors of the statistics
-        row_sc[buf * 128 + row] = live ? fabsf(rs32) * fmaxf(fabsf((float)row_a), 1.0f) : 0.0f;
-        row_w[buf * 128 + row] = live ? row_shift : 0.0;
+        row_sc[row] = live ? fabsf(rs32) * fmaxf(fabsf((float)row_a), 1.0f) : 0.0f;
+        row_w[row] = live ? row_shift : 0.0;
       }
       if (g_first >= n_groups && t == tiles_per_item - 1) {
         tc_fence_before_sync();
@@ -627,7 +631,6 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
       const uint32_t bytes = (uint32_t)live_rows * K * 4;
       const bool bulk = bulk_ok && (bytes & 15) == 0;
       fence_proxy_async_smem();
-      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store that read the OTHER buffer
       asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
       if (live_rows > 0) {
         float* gdst = (float*)p.fz.out + m0 * p.fz.ldo;
@@ -637,15 +640,16 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
           for (int i = et; i < live_rows * K; i += kStatThreads) gdst[(long long)(i / K) * p.fz.ldo + i % K] = sy[i];
         }
         if (kStats && lane < K) {
-          const float* sc = row_sc + buf * 128;
-          const double* wv = row_w + buf * 128;
           for (int r = ew; r < live_rows; r += kEpilogueWarps) {
             const float yv = sy[r * K + lane];
-            mx = max(mx, __float_as_uint(fabsf(yv) * sc[r]));   // |y| d max(1, mu) >= 0; a NaN sorts above +inf
-            sm = fma(wv[r], (double)yv, sm);
+            mx = max(mx, __float_as_uint(fabsf(yv) * row_sc[r]));   // |y| d max(1, mu) >= 0; a NaN sorts above +inf
+            sm = fma(row_w[r], (double)yv, sm);
           }
         }
       }
+      // the staging buffer is rewritten by the next tile: the bulk store must have read it, the statistics too
+      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
       if (ew == 0 && lane == 0) LMDEC_STAMP(10, (int)tile_no);
     }
   }
@@ -756,7 +760,7 @@ __device__ __forceinline__ void epilogue_dispatch(const GenoMmaParams& p, uint32
 // ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~100 cycles per MMA, profiles/r01).
 //   kPair: schedule (kPairNone / M / E / T);  kMiss: value + indicator planes (else K-block parity per issuer);
 //   kIlv: single tiles, issuer pair `issuer >> 1` takes the chunks of that parity within a work item.
-template <int kPair, bool kMiss, bool kIlv>
+template <int kPair, bool kMiss, bool kIlv, bool kRes = false>
 __device__ __forceinline__ void issuer_loop(const GenoMmaParams& p, int issuer, int lane, uint32_t tbase, uint32_t bar0,
                                             uint32_t smem_b_a, int n_work, int chunks_per_split) {
   constexpr bool quad = kIssuerWarps == 4 && kPair == kPairM;
@@ -803,7 +807,11 @@ __device__ __forceinline__ void issuer_loop(const GenoMmaParams& p, int issuer, 
     for (int c = c0; c < c1; ++c) {
       const bool my_chunk = !kIlv || ((c - c0) & 1) == hi;
       uint64_t bdesc0 = 0;
-      if (my_chunk) {
+      if (kRes) {
+        // resident image: chunk c of the (unsplit) contraction sits at c * stage_bytes, loaded once per kernel
+        if (tile_no == 0 && c == c0) mbar_wait_a(full_b, 0);
+        bdesc0 = bdesc_ring + (uint64_t)(((uint32_t)c * stage_bytes) >> 4);
+      } else if (my_chunk) {
         mbar_wait_a(full_b + 8 * b_stage, b_phase);
         if (issuer == 0 && lane == 0) LMDEC_STAMP(6, tr);   // B stage full seen by issuer 0
         bdesc0 = bdesc_ring + (uint64_t)((b_stage * stage_bytes) >> 4);
@@ -857,14 +865,16 @@ __device__ __forceinline__ void issuer_loop(const GenoMmaParams& p, int issuer, 
           a_phase ^= 1;
         }
       }
-      if (my_chunk) {
-        if (elect_one()) umma_commit_a(empty_b + 8 * b_stage);  // after every MMA that reads this B stage
-        __syncwarp();
-        if (issuer == 0 && lane == 0) LMDEC_STAMP(8, tr - 1);   // B stage released
-      }
-      if (++b_stage == b_stages) {
-        b_stage = 0;
-        b_phase ^= 1;
+      if (!kRes) {
+        if (my_chunk) {
+          if (elect_one()) umma_commit_a(empty_b + 8 * b_stage);  // after every MMA that reads this B stage
+          __syncwarp();
+          if (issuer == 0 && lane == 0) LMDEC_STAMP(8, tr - 1);   // B stage released
+        }
+        if (++b_stage == b_stages) {
+          b_stage = 0;
+          b_phase ^= 1;
+        }
       }
     }
     if (elect_one()) umma_commit_a(acc_full + 8 * set);
@@ -1042,7 +1052,15 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     }
   } else if (warp == kBLoaderWarp) {
     // ------------------------------------------------------------------ B image loader
-    if (lane == 0) {
+    if (lane == 0 && p.b_resident) {
+      // the whole image once: every work item of this CTA multiplies by the same n_chunks * stage_bytes
+      mbar_arrive_expect_tx_a(full_b, (uint32_t)p.n_chunks * stage_bytes);
+      for (int c = 0; c < p.n_chunks; ++c) {
+        const uint32_t dst = smem_b_a + (uint32_t)c * stage_bytes;
+        bulk_g2s_a(dst, p.image1 + (size_t)c * img_bytes, img_bytes, full_b);
+        if (p.n_img == 2) bulk_g2s_a(dst + img_bytes, p.image2 + (size_t)c * img_bytes, img_bytes, full_b);
+      }
+    } else if (lane == 0) {
       uint32_t b_stage = 0, b_phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int sp = w / p.m_units;
@@ -1073,6 +1091,13 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       if (p.pair == kPairM) LMDEC_ISSUE(kPairM, true, false);
       else if (p.pair == kPairE) LMDEC_ISSUE(kPairE, false, false);
       else if (p.pair == kPairT) LMDEC_ISSUE(kPairT, false, false);
+      else if (p.b_resident) {
+#define LMDEC_ISSUE_RES(MISS, ILV) \
+  issuer_loop<kPairNone, MISS, ILV, true>(p, issuer, lane, tbase, bar0, smem_b_a, n_work, chunks_per_split)
+        if (p.has_missing) { if (interleave) LMDEC_ISSUE_RES(true, true); else LMDEC_ISSUE_RES(true, false); }
+        else { if (interleave) LMDEC_ISSUE_RES(false, true); else LMDEC_ISSUE_RES(false, false); }
+#undef LMDEC_ISSUE_RES
+      }
       else if (p.has_missing) { if (interleave) LMDEC_ISSUE(kPairNone, true, true); else LMDEC_ISSUE(kPairNone, true, false); }
       else { if (interleave) LMDEC_ISSUE(kPairNone, false, true); else LMDEC_ISSUE(kPairNone, false, false); }
 #undef LMDEC_ISSUE

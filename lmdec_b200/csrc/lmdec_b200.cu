@@ -40,6 +40,7 @@ struct lmdec_ctx {
   int producer_groups = 2;   // 2: two producer groups on alternate tile-chunks when there is no missing data
   int producer_groups_missing = 1;   // the same with missing data (needs a decoded-A ring of >= 3 stages to pay)
   int acc_sets = 0;          // accumulator sets of single-tile work items: 0 = choose, 1, 2
+  int b_resident = 1;        // short unsplit contractions keep the whole operand image in shared memory
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
 };
@@ -1368,7 +1369,7 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
   }
   if (stats_emitted) *stats_emitted = p.fuse == 2;
   const size_t stage_bytes = (size_t)8 * N * 32 * p.n_img;
-  const size_t budget = 222 * 1024;  // 227 KB per CTA minus the static barriers / column constants (3 KB) and slack
+  const size_t budget = 223 * 1024 - 512;  // 227 KB per CTA minus the static barriers / column constants (4 KB), slack
   // shared memory behind the rings: the float32 epilogue's staging area (two output tiles, per-row factors, fold
   // scratch: epi32_stage_bytes), or -- float64 output with fused statistics -- the per-thread accumulators
   // [column slot][2][256] doubles of the round-1 epilogue
@@ -1398,12 +1399,24 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
     }
   }
   int tile_stages = kMaxTileStages, b_stages = 0;
-  for (; tile_stages >= 2; tile_stages /= 2) {
-    b_stages = (int)((budget - scratch - (size_t)tile_stages * kTileBytes) / stage_bytes);
-    if (b_stages >= 2) break;
+  // Short, unsplit contractions (A^T q with a few thousand samples): the WHOLE operand image stays in shared memory
+  // for the life of the CTA.  Every m-tile otherwise re-reads it from L2 -- 16 KB of image per 8 KB of genotypes, i.e.
+  // two thirds of the kernel's L2 -> SM traffic, which at ~42 B/cycle/SM is what bounds it (profiles/r02).
+  p.b_resident = 0;
+  const size_t image_bytes = (size_t)p.n_chunks * stage_bytes;
+  if (ctx.b_resident && !p.pair && p.splits == 1 && image_bytes + scratch + 4 * (size_t)kTileBytes <= budget) {
+    p.b_resident = 1;
+    tile_stages = (int)((budget - scratch - image_bytes) / kTileBytes);
+    if (tile_stages > kMaxTileStages) tile_stages = kMaxTileStages;
+    b_stages = p.n_chunks;      // (only sizes the region; the resident image has no ring)
+  } else {
+    for (; tile_stages >= 2; tile_stages /= 2) {
+      b_stages = (int)((budget - scratch - (size_t)tile_stages * kTileBytes) / stage_bytes);
+      if (b_stages >= 2) break;
+    }
+    if (b_stages > kMaxBStages) b_stages = kMaxBStages;
+    if (b_stages < 2 || tile_stages < 2) return fail("lmdec_geno_matmul: shared memory budget");
   }
-  if (b_stages > kMaxBStages) b_stages = kMaxBStages;
-  if (b_stages < 2 || tile_stages < 2) return fail("lmdec_geno_matmul: shared memory budget");
   p.stats_off = (int)((size_t)tile_stages * kTileBytes + b_stages * stage_bytes);
   p.b_stages = b_stages;
   p.tile_stages = tile_stages;
@@ -1775,6 +1788,7 @@ int lmdec_ctx_set(lmdec_ctx* ctx, int knob, int value) {
     case LMDEC_KNOB_PRODUCER_GROUPS: ctx->producer_groups = value == 1 ? 1 : 2; return 0;
     case LMDEC_KNOB_PRODUCER_GROUPS_MISSING: ctx->producer_groups_missing = value == 2 ? 2 : 1; return 0;
     case LMDEC_KNOB_ACC_SETS: ctx->acc_sets = value == 1 || value == 2 ? value : 0; return 0;
+    case LMDEC_KNOB_B_RESIDENT: ctx->b_resident = value != 0; return 0;
   }
   return fail("lmdec_ctx_set: unknown knob");
 }
@@ -1789,6 +1803,7 @@ int lmdec_ctx_get(const lmdec_ctx* ctx, int knob) {
     case LMDEC_KNOB_PRODUCER_GROUPS: return c.producer_groups;
     case LMDEC_KNOB_PRODUCER_GROUPS_MISSING: return c.producer_groups_missing;
     case LMDEC_KNOB_ACC_SETS: return c.acc_sets;
+    case LMDEC_KNOB_B_RESIDENT: return c.b_resident;
   }
   return -1;
 }
