@@ -105,8 +105,18 @@ struct FusedFinalize {
 constexpr int kTraceChunks = 64;
 __device__ long long g_trace[12][kTraceChunks];
 #define LMDEC_STAMP(row, idx) do { if (blockIdx.x == 0 && (idx) < kTraceChunks) g_trace[row][idx] = clock64(); } while (0)
+// cycles a role spends inside its barrier waits, summed over the kernel (CTA 0, one warp per role; tools/trace_mma.py):
+// the role that never waits is the one that paces the pipeline
+__device__ long long g_wait[16];
+#define LMDEC_WAITACC(slot, cond, stmt) do { if (blockIdx.x == 0 && (cond)) { long long t0_ = clock64(); stmt; \
+    wacc_[slot] += clock64() - t0_; } else { stmt; } } while (0)
+#define LMDEC_WAITDECL long long wacc_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define LMDEC_WAITOUT(slot, cond) do { if (blockIdx.x == 0 && (cond)) g_wait[slot] = wacc_[slot]; } while (0)
 #else
 #define LMDEC_STAMP(row, idx) do { } while (0)
+#define LMDEC_WAITACC(slot, cond, stmt) do { stmt; } while (0)
+#define LMDEC_WAITDECL do { } while (0)
+#define LMDEC_WAITOUT(slot, cond) do { } while (0)
 #endif
 
 struct GenoMmaParams {
@@ -184,8 +194,12 @@ __device__ __forceinline__ void produce_chunk(const uint4 (&raw)[KB / 2], uint32
       decode16<kMiss>(regs[2 * j], v, m);
       decode16<kMiss>(regs[2 * j + 1], v + 4, m + 4);
       const int kb = kb0 + 2 * i + j;
+#ifdef LMDEC_ABL_NOSTTM     // ablation (timing only): no TMEM stores of the decoded operand
+      if (v[0] == 0x12345678u && m[7] == 0x9abcdef1u) tmem_st8(a_stage_addr + kb * 8, v);
+#else
       tmem_st8(a_stage_addr + kb * 8, v);
       if (kMiss) tmem_st8(a_stage_addr + 64 + kb * 8, m);
+#endif
     }
   }
 }
@@ -550,6 +564,7 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
   const int shift1 = p.has_missing ? kMissShift : kValueShift;
   const int tiles_per_item = p.pair ? 2 : 1;
   const bool bulk_ok = p.fz.ldo == K && (reinterpret_cast<uintptr_t>(p.fz.out) & 15) == 0;
+  LMDEC_WAITDECL;
   uint32_t mx = 0u;      // running column statistics of this thread's (column, row class): max as float bits, sum
   double sm = 0.0;
   uint32_t tile_no = 0;
@@ -557,7 +572,7 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
     const int unit = w % p.m_units;
     const uint32_t set = p.pair ? 0u : tile_no % acc_sets;
     const uint32_t set_phase = p.pair ? (tile_no & 1) : ((tile_no / acc_sets) & 1);
-    mbar_wait_relaxed_a(acc_full + 8 * set, set_phase);
+    LMDEC_WAITACC(0, ew == 0 && lane == 0, mbar_wait_relaxed_a(acc_full + 8 * set, set_phase));
     if (ew == 0 && lane == 0) LMDEC_STAMP(9, (int)tile_no);
     tc_fence_after_sync();
     for (int t = 0; t < tiles_per_item; ++t) {
@@ -653,6 +668,7 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
       if (ew == 0 && lane == 0) LMDEC_STAMP(10, (int)tile_no);
     }
   }
+  LMDEC_WAITOUT(0, ew == 0 && lane == 0);
   if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (kStats) {
     fold_mx[ew * 32 + lane] = mx;
@@ -787,6 +803,7 @@ __device__ __forceinline__ void issuer_loop(const GenoMmaParams& p, int issuer, 
   const uint64_t bdesc_ring = make_smem_desc(smem_b_a, lbo, 128) + (uint64_t)((img * img_bytes) >> 4);
   const uint32_t a_ring = tbase + (uint32_t)p.a_ring_col0 + plane * 64;
   const uint32_t kb_step = (uint32_t)(2 * N);  // one K-block of the image, in 16-byte units
+  LMDEC_WAITDECL;
   uint32_t a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
   uint32_t tile_no = 0;
   int tr = 0;
@@ -797,7 +814,7 @@ __device__ __forceinline__ void issuer_loop(const GenoMmaParams& p, int issuer, 
     const int c1 = min(c0 + chunks_per_split, p.n_chunks);
     const uint32_t set = kPair ? 0u : tile_no % acc_sets;
     const uint32_t set_phase = kPair ? (tile_no & 1) : ((tile_no / acc_sets) & 1);
-    mbar_wait_a(acc_empty + 8 * set, set_phase ^ 1);
+    LMDEC_WAITACC(1, issuer == 0 && lane == 0, mbar_wait_a(acc_empty + 8 * set, set_phase ^ 1));
     tc_fence_after_sync();
     uint32_t accumulate[2] = {0, 0};
     // interleaved pairs: pair 0 owns the first chunk of the work item and its first MMA overwrites the accumulator;
@@ -812,7 +829,7 @@ __device__ __forceinline__ void issuer_loop(const GenoMmaParams& p, int issuer, 
         if (tile_no == 0 && c == c0) mbar_wait_a(full_b, 0);
         bdesc0 = bdesc_ring + (uint64_t)(((uint32_t)c * stage_bytes) >> 4);
       } else if (my_chunk) {
-        mbar_wait_a(full_b + 8 * b_stage, b_phase);
+        LMDEC_WAITACC(2, issuer == 0 && lane == 0, mbar_wait_a(full_b + 8 * b_stage, b_phase));
         if (issuer == 0 && lane == 0) LMDEC_STAMP(6, tr);   // B stage full seen by issuer 0
         bdesc0 = bdesc_ring + (uint64_t)((b_stage * stage_bytes) >> 4);
       }
@@ -820,14 +837,14 @@ __device__ __forceinline__ void issuer_loop(const GenoMmaParams& p, int issuer, 
       for (int t = 0; t < tiles_per_item; ++t) {
         const bool mine = my_chunk && (quad ? (t == hi) : (kPair != kPairT || t == me));
         if (mine) {
-          mbar_wait_a(full_a + 8 * a_stage, a_phase);
+          LMDEC_WAITACC(3, issuer == 0 && lane == 0, mbar_wait_a(full_a + 8 * a_stage, a_phase));
           if (issuer == 0 && lane == 0) LMDEC_STAMP(4, tr);   // A stage full seen by issuer 0
           tc_fence_after_sync();
           const uint32_t slot = kPair ? (uint32_t)t : set;
           const uint32_t d_addr = tbase + (kPair == kPairT ? slot : slot * 2 + me) * acc_w;
           const uint32_t a_addr = a_ring + a_stage * a_stage_cols;
           if (kIlv && !ordered) {
-            mbar_wait_a(first_done + 8 * (set * 2 + me), set_phase);
+            LMDEC_WAITACC(4, issuer == 2 && lane == 0, mbar_wait_a(first_done + 8 * (set * 2 + me), set_phase));
             tc_fence_after_sync();
             ordered = true;
           }
@@ -881,6 +898,10 @@ __device__ __forceinline__ void issuer_loop(const GenoMmaParams& p, int issuer, 
     __syncwarp();
     if (issuer == 0 && lane == 0) LMDEC_STAMP(7, (int)tile_no);   // work item's MMAs issued
   }
+  LMDEC_WAITOUT(1, issuer == 0 && lane == 0);
+  LMDEC_WAITOUT(2, issuer == 0 && lane == 0);
+  LMDEC_WAITOUT(3, issuer == 0 && lane == 0);
+  LMDEC_WAITOUT(4, issuer == 2 && lane == 0);
 }
 
 template <int kGroups>
@@ -951,6 +972,9 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tbase = tmem_base_s;
+#ifdef LMDEC_TRACE
+  if (blockIdx.x == 0 && tid == 0) g_wait[14] = clock64();
+#endif
 
   const int n_work = p.m_units * p.splits;
   const int chunks_per_split = (p.n_chunks + p.splits - 1) / p.splits;
@@ -968,6 +992,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     uint32_t a_stage = 0, a_phase = 0, t_stage = 0, t_phase = 0;
     int tr = 0;
     const bool tracer = pw == 0 && lane == 0;
+    LMDEC_WAITDECL;
     (void)tr; (void)tracer;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int sp = w / p.m_units;
@@ -986,29 +1011,44 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
           }
           continue;
         }
-        mbar_wait_a(full_t + 8 * t_stage, t_phase);
+#ifndef LMDEC_ABL_NOTILESYNC
+        LMDEC_WAITACC(5, tracer, mbar_wait_a(full_t + 8 * t_stage, t_phase));
+#endif
         if (tracer) LMDEC_STAMP(0, tr);   // tile arrived
         const uint32_t src = smem_t_a + t_stage * kTileBytes + my_off;
         uint4 raw[kKb / 2];
+#ifdef LMDEC_ABL_NOLDS
+#pragma unroll
+        for (int i = 0; i < kKb / 2; ++i) raw[i] = make_uint4(src, src + 1, src + 2, src + 3);
+#else
 #pragma unroll
         for (int i = 0; i < kKb / 2; ++i) raw[i] = lds128(src + i * 2048);
-        mbar_wait_a(empty_a + 8 * a_stage, a_phase ^ 1);
+#endif
+        LMDEC_WAITACC(6, tracer, mbar_wait_a(empty_a + 8 * a_stage, a_phase ^ 1));
         if (tracer) LMDEC_STAMP(1, tr);   // A stage free
+#ifndef LMDEC_ABL_NOFENCE
         tc_fence_after_sync();
+#endif
         const uint32_t a_addr = lane_addr + kARingCol0 + a_stage * a_stage_cols;
         if (p.has_missing)
           produce_chunk<true, kKb>(raw, a_addr, kKb * half);
         else
           produce_chunk<false, kKb>(raw, a_addr, kKb * half);
         if (tracer) LMDEC_STAMP(2, tr);   // decode + tcgen05.st issued
+#ifndef LMDEC_ABL_NOFENCE
         tmem_wait_st();
+#endif
         if (tracer) LMDEC_STAMP(3, tr);   // stores complete
         ++tr;
+#ifndef LMDEC_ABL_NOFENCE
         tc_fence_before_sync();
+#endif
         __syncwarp();
         if (lane == 0) {
           mbar_arrive_a(full_a + 8 * a_stage);
+#ifndef LMDEC_ABL_NOTILESYNC
           mbar_arrive_a(empty_t + 8 * t_stage);  // raw[] is consumed: the tile slot can be refilled
+#endif
         }
         if (++a_stage == (uint32_t)a_stages) {
           a_stage = 0;
@@ -1020,12 +1060,19 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
         }
       }
     }
+    LMDEC_WAITOUT(5, tracer);
+    LMDEC_WAITOUT(6, tracer);
   } else if (warp == kTileLoaderWarp) {
     // ------------------------------------------------------------------ packed-tile loader (TMA bulk copies)
+#ifdef LMDEC_ABL_NOTILESYNC
+    if (false) {
+#else
     if (lane == 0) {
+#endif
       uint32_t t_stage = 0, t_phase = 0;
       int ld_no = 0;
       (void)ld_no;
+      LMDEC_WAITDECL;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int unit = w % p.m_units, sp = w / p.m_units;
         const int c0 = sp * chunks_per_split;
@@ -1037,11 +1084,15 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
         const uint8_t* tile_b = p.store + ((size_t)mt1 * p.store_kc) * kTileBytes;
         for (int c = c0; c < c1; ++c) {
           for (int t = 0; t < tiles_per_item; ++t) {
-            mbar_wait_relaxed_a(empty_t + 8 * t_stage, t_phase ^ 1);
+            LMDEC_WAITACC(7, true, mbar_wait_relaxed_a(empty_t + 8 * t_stage, t_phase ^ 1));
             LMDEC_STAMP(11, ld_no++);                                   // tile slot free, copy issued
+#ifdef LMDEC_ABL_NOLOAD     // ablation (timing only): the packed-tile ring cycles without any HBM traffic
+            mbar_arrive_a(full_t + 8 * t_stage);
+#else
             mbar_arrive_expect_tx_a(full_t + 8 * t_stage, kTileBytes);
             bulk_g2s_a(smem_t_a + t_stage * kTileBytes, (t ? tile_b : tile_a) + (size_t)c * kTileBytes, kTileBytes,
                        full_t + 8 * t_stage);
+#endif
             if (++t_stage == (uint32_t)p.tile_stages) {
               t_stage = 0;
               t_phase ^= 1;
@@ -1049,8 +1100,10 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
           }
         }
       }
+      LMDEC_WAITOUT(7, true);
     }
   } else if (warp == kBLoaderWarp) {
+    LMDEC_WAITDECL;
     // ------------------------------------------------------------------ B image loader
     if (lane == 0 && p.b_resident) {
       // the whole image once: every work item of this CTA multiplies by the same n_chunks * stage_bytes
@@ -1067,7 +1120,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
         const int c0 = sp * chunks_per_split;
         const int c1 = min(c0 + chunks_per_split, p.n_chunks);
         for (int c = c0; c < c1; ++c) {
-          mbar_wait_relaxed_a(empty_b + 8 * b_stage, b_phase ^ 1);
+          LMDEC_WAITACC(8, true, mbar_wait_relaxed_a(empty_b + 8 * b_stage, b_phase ^ 1));
           const uint32_t dst = smem_b_a + b_stage * stage_bytes;
           mbar_arrive_expect_tx_a(full_b + 8 * b_stage, stage_bytes);
           bulk_g2s_a(dst, p.image1 + (size_t)c * img_bytes, img_bytes, full_b + 8 * b_stage);
@@ -1080,6 +1133,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
         }
       }
     }
+    LMDEC_WAITOUT(8, lane == 0);
   } else if (warp >= kIssuerWarp0 && warp < kIssuerWarp0 + kIssuerWarps) {
     // ------------------------------------------------------------------ MMA issuers
     if (warp - kIssuerWarp0 < n_issuers) {
@@ -1114,6 +1168,9 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   }
   tc_fence_before_sync();
   __syncthreads();
+#ifdef LMDEC_TRACE
+  if (blockIdx.x == 0 && tid == 0) g_wait[15] = clock64() - g_wait[14];
+#endif
   if (warp == 0) tmem_dealloc<512>(tbase);
 }
 

@@ -1760,6 +1760,15 @@ int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const in
 int lmdec_trace_read(long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 12 * kTraceChunks);
 }
+// wait-time accounting of CTA 0 (see LMDEC_WAITACC); reset != 0 zeroes it after the read
+int lmdec_wait_read(long long* host_out, int reset) {
+  int rc = (int)cudaMemcpyFromSymbol(host_out, g_wait, sizeof(long long) * 16);
+  if (reset) {
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_wait, z, sizeof(z));
+  }
+  return rc;
+}
 #endif
 
 lmdec_ctx* lmdec_ctx_create(void) { return new lmdec_ctx(); }
