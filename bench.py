@@ -5,13 +5,19 @@
   python bench.py --impl reference --gpus N ...            the reference's CPU path (NumPy oracle port, host cores)
 
 Workload at every N: BASELINE.json configs[1] per GPU -- a 1000G-shaped 2,504 x 1,000,000 genotype shard with 5 % iid
-missing (mean-imputed), centre + binomial scale, k = 10 (+ buffer 10 => K = 20).  At N > 1 the samples are row-sharded
-(global matrix (N*2504) x 1M, weak scaling) and the only collectives are the p x K all-reduce of A^T q and the K x K
-Gram all-reduce (NCCL).
+missing (mean-imputed), centre + binomial scale, k = 10 (+ buffer 10 => K = 20); weak scaling.  The multi-GPU
+decomposition follows the shape (`--shard auto`, stated in config.parallelism): with n << p (this workload) the SNP axis
+is sharded -- every GPU holds all samples of its SNP block, A^T q stays local, the only collective per step is the
+all-reduce of A t (n x K float64, 400 KB); `--shard rows` forces the sample-row decomposition (all-reduce of A^T q,
+p x K float32, and of the K x K Gram matrices), which is the right cut when the sample axis is the long one.
 
 A "step" is one full iteration of PowerMethod.svd's loop body (accuracy: CholeskyQR2 + K x K SVD + q-vals; step:
-A^T q, A t) on data resident in HBM.  `value` = 4 n p K flops per step / time.  `e2e` runs the same Gram-operator
-application through the public operator API with HOST operands: q (pinned host) -> H2D -> A.T.dot -> A.dot -> D2H.
+A^T q, A t) on data resident in HBM.  `value` = 4 n p K flops per step / time.  `e2e` is the SAME full step through the
+public API with the iterate in HOST memory: x (pinned host) -> H2D -> orthonormalise -> A^T q -> A t -> / n -> D2H.
+
+`--target` (also run by default at N = 8, key "target" of the JSON line): the north-star problem, top-10 PCA of a
+100,000 x 500,000 genotype matrix, samples row-sharded over the N GPUs (strong scaling), run to convergence, with S / V
+checked against the oracle's arithmetic on a column slab.
 """
 from __future__ import annotations
 
@@ -37,9 +43,13 @@ def peaks():
     if os.path.exists(path):
         with open(path) as f:
             d = json.load(f)
-        return {"hbm_gbs": d["hbm_gbs"], "tensor_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
-                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
-    return {"hbm_gbs": 6650.0, "tensor_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+        # the timed region is tens of milliseconds at full clocks (see "clocks"): the BURST cuBLAS figure is the
+        # denominator; the sustained one (seconds-long loop under the power cap) is reported beside it
+        return {"hbm_gbs": d["hbm_gbs"], "tensor_tflops": d["bf16_tflops"],
+                "tensor_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json, burst bf16: kernel timed in a short region at full clocks)"}
+    return {"hbm_gbs": 6650.0, "tensor_tflops": 1590.0, "tensor_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md, burst)"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -100,7 +110,16 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def resolve_shard(shard):
+    """`auto`: shard the LONG axis.  configs[1] has n = 2,504 samples against p = 1,000,000 SNPs per GPU, so the SNP axis
+    is sharded (sample-row shards would all-reduce the p x K side, 80 MB per step, for 0.3 ms of compute)."""
+    if shard == "auto":
+        return "rows" if N_ROWS >= N_COLS else "snps"
+    return shard
+
+
 def workload_config(n_gpus, shard="snps"):
+    shard = resolve_shard(shard)
     rows = shard == "rows"
     return {"workload": f"configs[1]: 1000G-shaped {N_ROWS}x{N_COLS} 2-bit genotypes per GPU, 5% missing "
                         f"(mean-impute), center+binom scale, PowerMethod k={K_TOP} buffer={BUFFER} (K=20), "
@@ -109,8 +128,10 @@ def workload_config(n_gpus, shard="snps"):
             "parallelism": "single GPU" if n_gpus == 1 else
                            (f"samples row-sharded x{n_gpus}: all-reduce of A^T q (p x K float32) and of the Gram matrices"
                             if rows else
-                            f"SNPs sharded x{n_gpus} (every GPU holds all {N_ROWS} samples of its {N_COLS} SNPs): "
-                            f"one all-reduce of A t (n x K float64, 400 KB) per step"),
+                            f"SNPs sharded x{n_gpus} (chosen by shape: n = {N_ROWS} << p; every GPU holds all "
+                            f"{N_ROWS} samples of its {N_COLS} SNPs): one all-reduce of A t (n x K float64, 400 KB) "
+                            f"per step.  The north-star's sample-row decomposition is measured on the north-star "
+                            f"problem (key `target`)"),
             "l2": "inputs larger than L2 (2 x 626 MB tile stores per step vs 126 MB L2)"}
 
 
@@ -209,6 +230,105 @@ def make_shard(torch, device, n, p, miss, seed):
     return store
 
 
+def run_target(torch, dist, device, world, rank, group, planes):
+    """North-star problem (BASELINE.json): top-10 PCA of a 100,000 x 500,000 genotype matrix, samples ROW-sharded over
+    the N GPUs of the box (strong scaling), PowerMethod run to convergence (q-vals, tol 1e-4).  Collectives per
+    iteration: all-reduce of A^T q (p x K float32, 40 MB) and of the K x K Gram matrices (CholeskyQR2).  The converged
+    factors are checked against the ORACLE's arithmetic on a column slab: (A^T U)[J] computed on the host in float64 from
+    the decoded genotypes must equal V[:, J]^T S sqrt(n)."""
+    from lmdec_b200 import PowerMethod
+    from lmdec_b200.store import GenotypeOperator
+    n, p, k, buffer, slab = 100_000, 500_000, 10, 10, 512
+    K = k + buffer
+    bounds = [n * r // world for r in range(world + 1)]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    t0 = time.time()
+    store = make_shard(torch, device, hi - lo, p, 0.0, seed=7000 + rank)
+    if world > 1:
+        store.group, store.n_global, store.row_offset = group, n, lo
+    mean, std = store.moments("binom")
+    op = GenotypeOperator(store, mean, 1.0 / std, planes=planes)
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    x0 = np.random.default_rng(42).standard_normal((n, K))[lo:hi]
+    kw = dict(k=k, buffer=buffer, tol=1e-4, scoring_method="q-vals", sub_svd_start=False, lmbd=0, max_iter=200)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    PowerMethod(**dict(kw, max_iter=3)).svd(op, x0=x0, verbose=False)      # warm-up (allocations, cuBLAS handles)
+    barrier()
+    pm = PowerMethod(**kw)
+    ts = time.time()
+    U, S, V = pm.svd(op, x0=x0, verbose=False)
+    barrier()
+    seconds = time.time() - ts
+    # steady-state iteration rate (device timed, max over ranks)
+    pm2 = PowerMethod(**dict(kw, tol=1e-30, max_iter=10 ** 6))
+    pm2._reset_history()
+    x = pm2._initialization(op, x0=x0)
+    for _ in range(3):
+        pm2._solution_accuracy(x)
+        x = pm2._solution_step(x)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 10
+    e0.record()
+    for _ in range(steps):
+        pm2._solution_accuracy(x)
+        x = pm2._solution_step(x)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_iter = float(ms.item())
+    # ---- oracle check on the first `slab` SNPs: gather U (n x k) and the decoded slab (n x slab) on rank 0
+    u_loc = U.t.contiguous()
+    codes = store.to_dense(transpose=True, rows=slab).T.contiguous()            # [n_loc, slab] int8
+    if world > 1:
+        sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
+        u_all = [torch.empty((sz, k), dtype=u_loc.dtype, device=device) for sz in sizes]
+        c_all = [torch.empty((sz, slab), dtype=torch.int8, device=device) for sz in sizes]
+        dist.all_gather(u_all, u_loc)
+        dist.all_gather(c_all, codes)
+        u_full, c_full = torch.cat(u_all), torch.cat(c_all)
+    else:
+        u_full, c_full = u_loc, codes
+    out = None
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import lmdec_oracle as oracle
+        g = c_full.cpu().numpy().astype(np.float64)
+        ref = oracle.make_snp_array(g, std_method="binom")
+        w_ref = np.asarray(ref.T.dot(u_full.cpu().numpy()))                     # (A^T U)[J], float64 on the host
+        S_np, V_np = np.asarray(S), np.asarray(V)
+        w_gpu = V_np[:, :slab].T * (S_np * np.sqrt(n))
+        sign = np.sign(np.sum(w_ref * w_gpu, axis=0))
+        err = float(np.linalg.norm(w_ref - w_gpu * sign) / np.linalg.norm(w_ref))
+        s_slab = np.linalg.norm(w_ref, axis=0) / np.linalg.norm(V_np[:, :slab], axis=1) / np.sqrt(n)
+        flops_iter = 4.0 * n * p * K
+        pk = peaks()
+        t_roof = max(flops_iter / world / (pk["tensor_tflops"] * 1e12), (n / world) * p / 4 / (pk["hbm_gbs"] * 1e9))
+        out = {"problem": "top-10 PCA of a 100,000 x 500,000 2-bit genotype matrix (no missing codes), centre + binom "
+                          "scale, K = 20, q-vals tol 1e-4, x0 = default_rng(42)",
+               "parallelism": "single GPU" if world == 1 else
+                              f"samples row-sharded x{world} (strong scaling): all-reduce of A^T q (p x K float32, 40 MB) "
+                              f"and of the K x K Gram matrices per iteration",
+               "n_gpus": world, "iterations": int(pm.num_iter), "seconds_to_converged": seconds,
+               "tflops_to_converged": flops_iter * pm.num_iter / seconds / 1e12,
+               "ms_per_iteration": ms_iter, "tflops": flops_iter / (ms_iter * 1e-3) / 1e12,
+               "roofline_frac_per_gpu": t_roof / (ms_iter * 1e-3), "store_build_seconds": t_build,
+               "S": [float(v) for v in S_np],
+               "oracle_slab_check": {"slab_snps": slab, "rel_err_AtU_vs_V_S_sqrt_n": err,
+                                     "S_from_oracle_slab_rel_dev": float(np.max(np.abs(s_slab - S_np) / S_np))}}
+    del op, store
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -229,7 +349,7 @@ def run_ours(args):
         group = dist.group.WORLD
     lib = _capi.load()
     K = K_TOP + BUFFER
-    by_rows = args.shard == "rows" and world > 1
+    by_rows = resolve_shard(args.shard) == "rows" and world > 1
     n_global = N_ROWS * world if by_rows else N_ROWS
     p_global = N_COLS if by_rows else N_COLS * world
 
@@ -291,14 +411,21 @@ def run_ours(args):
     mma_total_ms, mma_launches = store.ctx.timing_read()
     store.ctx.timing(False)
 
-    # ---- e2e: public operator API with host operands (pinned), H2D + D2H inside the timed region
-    q_host = torch.from_numpy(np.linalg.qr(x0_full[my_rows])[0]).pin_memory()
+    # ---- e2e: the SAME full step (accuracy + step of PowerMethod.svd's loop) with the iterate in pinned HOST memory:
+    # H2D of x, CholeskyQR2 + K x K SVD + q-vals, A^T q, A t, / n, D2H of the next iterate -- all inside the timed region
+    x_host = x.detach().cpu().pin_memory()
     out_host = torch.empty((N_ROWS, K), dtype=torch.float64).pin_memory()
+    pm_e = PowerMethod(k=K_TOP, buffer=BUFFER, tol=1e-30, scoring_method="q-vals", sub_svd_start=False, lmbd=0,
+                       max_iter=10 ** 6)
+    pm_e._reset_history()
+    pm_e._initialization(op, x0=x_host)
 
     def e2e_step():
-        qd = q_host.to(device, non_blocking=True)
-        xd = op.dot(op.T.dot(qd))
-        out_host.copy_(xd.t, non_blocking=True)
+        xd = x_host.to(device, non_blocking=True)
+        pm_e._solution_accuracy(xd)
+        out_host.copy_(pm_e._solution_step(xd), non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the user holds the result on the host
+        x_host.copy_(out_host)
 
     for _ in range(3):
         e2e_step()
@@ -331,13 +458,25 @@ def run_ours(args):
         svd_info = {"seconds": time.time() - ts, "iterations": pm2.num_iter, "tol": 1e-4,
                     "store_build_seconds": t_build}
 
+    # ---- the north-star problem (strong scaling over the N GPUs): see run_target
+    target = None
+    if args.target:
+        del op, store, pm, pm_e
+        torch.cuda.empty_cache()
+        try:
+            target = run_target(torch, dist, device, world, rank, group, args.planes)
+        except Exception as e:      # never lose the headline line to the extra
+            target = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         pk = peaks()
         avg_kernel_ms = mma_total_ms / max(mma_launches, 1)
         flops_launch = 2.0 * N_ROWS * N_COLS * K          # per GPU, per geno_mma launch (one of the two products)
         achieved = flops_launch / (avg_kernel_ms * 1e-3) / 1e12
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01", "geno_mma_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02", "geno_mma_traffic.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r01", "geno_mma_traffic.json")
         if os.path.exists(tpath) and args.planes == 3:
             with open(tpath) as f:
                 traffic = json.load(f)["dram_bytes_per_launch_mean"]   # ncu --set full, dram read + write, per launch
@@ -352,10 +491,14 @@ def run_ours(args):
             "e2e": {"value": flops_step / (e2e_ms_step * 1e-3) / 1e12, "unit": "TFLOP/s",
                     "h2d_bytes_per_step": N_ROWS * K * 8, "d2h_bytes_per_step": N_ROWS * K * 8,
                     "ms_per_step": e2e_ms_step,
-                    "api": "x = op.dot(op.T.dot(q)) with q, x in pinned host memory (GenotypeOperator from make_snp_array)"},
+                    "api": "one full PowerMethod iteration (accuracy: CholeskyQR2 + K x K SVD + q-vals; step: "
+                           "x <- A (A^T q) / n through GenotypeOperator) with the iterate x in pinned host memory: "
+                           "H2D of x and D2H of the next x every step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tensor_tflops"], "traffic": traffic,
+                         "frac_of_sustained_peak": achieved / pk["tensor_tflops_sustained"],
+                         "step_frac": flops_step / world / (ms_step * 1e-3) / 1e12 / pk["tensor_tflops"],
                          "kernel": "geno_mma_kernel (2 launches per step: A^T q and A t)",
                          "avg_launch_ms": avg_kernel_ms, "launches_timed": mma_launches,
                          "kernel_share_of_step": mma_total_ms / ms_total,
@@ -366,6 +509,8 @@ def run_ours(args):
                          "t_tensor_ms": t_tensor * 1e3, "t_hbm_ms": t_hbm * 1e3, "peak_source": pk["source"]},
             "svd": svd_info,
         }
+        if target is not None:
+            line["target"] = target
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = {k: v for k, v in cpu_step_throughput(3, 1).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
@@ -381,8 +526,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--planes", type=int, default=3)
-    ap.add_argument("--shard", default="snps", choices=["snps", "rows"],
-                    help="multi-GPU decomposition: SNP shards (default; n << p) or sample-row shards")
+    ap.add_argument("--shard", default="auto", choices=["auto", "snps", "rows"],
+                    help="multi-GPU decomposition: by shape (auto: SNP shards for this n << p workload), or forced")
+    ap.add_argument("--no-target", dest="target", action="store_false",
+                    help="skip the north-star problem (100k x 500k, row-sharded, run to convergence)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps")
     args = ap.parse_args()
