@@ -54,7 +54,8 @@ enum lmdec_knob {
   LMDEC_KNOB_PRODUCER_GROUPS = 4, /* 2: two decode groups on alternate tile-chunks when no code is missing; 1: one */
   LMDEC_KNOB_PRODUCER_GROUPS_MISSING = 5, /* the same when codes are missing (only with a decoded-operand ring >= 3 deep) */
   LMDEC_KNOB_ACC_SETS = 6,        /* accumulator sets of single-tile work items: 0 = choose, 1 (deeper operand ring), 2 */
-  LMDEC_KNOB_B_RESIDENT = 7       /* 1: short unsplit contractions keep the whole operand image in shared memory; 0: ring */
+  LMDEC_KNOB_B_RESIDENT = 7,      /* 1: short unsplit contractions keep the whole operand image in shared memory; 0: ring */
+  LMDEC_KNOB_ROUND_ROBIN = 8      /* 1: without missing codes 4 MMA issuers take whole chunks round-robin; 0: K-block parity */
 };
 int lmdec_ctx_set(lmdec_ctx* ctx, int knob, int value);
 int lmdec_ctx_get(const lmdec_ctx* ctx, int knob);

@@ -92,7 +92,7 @@ def load():
 
 # knobs of lmdec_ctx_set (include/lmdec_b200.h, enum lmdec_knob)
 (KNOB_SM_RESERVE, KNOB_PAIR_MODE, KNOB_PAIR_MIN_CHUNKS, KNOB_ISSUER_GROUPS, KNOB_PRODUCER_GROUPS,
- KNOB_PRODUCER_GROUPS_MISSING, KNOB_ACC_SETS, KNOB_B_RESIDENT) = range(8)
+ KNOB_PRODUCER_GROUPS_MISSING, KNOB_ACC_SETS, KNOB_B_RESIDENT, KNOB_ROUND_ROBIN) = range(9)
 
 
 class Context:
@@ -109,7 +109,8 @@ class Context:
                 self.set(KNOB_PAIR_MIN_CHUNKS, v)
         for env, knob in (("LMDEC_ISSUER_GROUPS", KNOB_ISSUER_GROUPS), ("LMDEC_ACC_SETS", KNOB_ACC_SETS),
                           ("LMDEC_PRODUCER_GROUPS_MISSING", KNOB_PRODUCER_GROUPS_MISSING),
-                          ("LMDEC_PRODUCER_GROUPS", KNOB_PRODUCER_GROUPS), ("LMDEC_B_RESIDENT", KNOB_B_RESIDENT)):
+                          ("LMDEC_PRODUCER_GROUPS", KNOB_PRODUCER_GROUPS), ("LMDEC_B_RESIDENT", KNOB_B_RESIDENT),
+                          ("LMDEC_ROUND_ROBIN", KNOB_ROUND_ROBIN)):
             if os.environ.get(env):
                 self.set(knob, int(os.environ[env]))
 

@@ -144,6 +144,8 @@ struct GenoMmaParams {
   int m_units;             // work items per split: m_tiles, or ceil(m_tiles / 2) in pair mode
   int stats_off;           // byte offset of the statistics accumulators in dynamic shared memory (fuse == 2)
   int stats_cols;          // column slots per epilogue thread
+  int rr;                  // no missing data: 4 issuers take whole chunks round-robin, ONE accumulator per tile (issuer_loop_rr)
+  int one_acc;             // one accumulator per tile (pair mode T, rr): the epilogue reads acc0 only
   int b_resident;          // the whole operand image stays in shared memory (short, unsplit contractions): no B ring
   int epi_staged;          // float32 output: the staged epilogue (epilogue_loop32) has its staging area at stats_off
   int issuer_groups;       // 2: chunk-interleaved issuer pairs (single-tile work items)
@@ -182,9 +184,40 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
+// Width of the tcgen05.st that moves a thread's decoded bytes into the TMEM operand ring: 8, 16 or 32 columns (32-bit
+// registers) per instruction.  The producers' store phase (~390 cycles per chunk for 64 KB: profiles/r02) is what paces
+// the kernel; fewer, wider stores move the same bytes with less per-instruction overhead.
+#ifndef LMDEC_STTM_W
+#define LMDEC_STTM_W 16
+#endif
 template <bool kMiss, int KB>
 __device__ __forceinline__ void produce_chunk(const uint4 (&raw)[KB / 2], uint32_t a_stage_addr, int kb0) {
   // this thread's bytes = K-blocks kb0 .. kb0 + KB of the chunk; raw[i] = 64 codes = 2 K-blocks
+#if LMDEC_STTM_W == 32
+#pragma unroll
+  for (int h = 0; h < KB / 4; ++h) {       // 4 K-blocks = 32 columns per plane per store
+    uint32_t v[32], m[32];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint4 rw = raw[2 * h + i];
+      const uint32_t regs[4] = {rw.x, rw.y, rw.z, rw.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) decode16<kMiss>(regs[j], v + 16 * i + 4 * j, m + 16 * i + 4 * j);
+    }
+    tmem_st32(a_stage_addr + (kb0 + 4 * h) * 8, v);
+    if (kMiss) tmem_st32(a_stage_addr + 64 + (kb0 + 4 * h) * 8, m);
+  }
+#elif LMDEC_STTM_W == 16
+#pragma unroll
+  for (int i = 0; i < KB / 2; ++i) {       // 2 K-blocks = 16 columns per plane per store
+    const uint32_t regs[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+    uint32_t v[16], m[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) decode16<kMiss>(regs[j], v + 4 * j, m + 4 * j);
+    tmem_st16(a_stage_addr + (kb0 + 2 * i) * 8, v);
+    if (kMiss) tmem_st16(a_stage_addr + 64 + (kb0 + 2 * i) * 8, m);
+  }
+#else
 #pragma unroll
   for (int i = 0; i < KB / 2; ++i) {
     const uint32_t regs[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
@@ -202,6 +235,7 @@ __device__ __forceinline__ void produce_chunk(const uint4 (&raw)[KB / 2], uint32
 #endif
     }
   }
+#endif
 }
 
 // Epilogue of one warp (one TMEM lane quarter, thread = output row).  Accumulator column n = k*P + plane, so the P
@@ -287,7 +321,7 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
     for (int t = 0; t < tiles_per_item; ++t) {
       const int mt = p.pair ? 2 * unit + t : unit;
       const uint32_t slot = p.pair ? (uint32_t)t : set;
-      const uint32_t acc0 = lane_addr + (p.pair == kPairT ? slot : slot * 2) * acc_w, acc1 = acc0 + acc_w;
+      const uint32_t acc0 = lane_addr + (p.one_acc ? slot : slot * 2) * acc_w, acc1 = acc0 + acc_w;
       const long long m = (long long)mt * 128 + row;
       const bool live = mt < p.m_tiles && m < p.m_limit;
       long long* dst0 = p.out0 + m * K;
@@ -315,7 +349,7 @@ __device__ __forceinline__ void epilogue_loop(const GenoMmaParams& p, uint32_t t
         const uint32_t col = (uint32_t)g * 8 * P;
 #pragma unroll
         for (int i = 0; i < P; ++i) tmem_ld8p(acc0 + col + i * 8, r0 + 8 * i);
-        if (p.pair == kPairT) {
+        if (p.one_acc) {
 #pragma unroll
           for (int i = 0; i < 8 * P; ++i) r1[i] = 0;  // one accumulator per tile
         } else {
@@ -578,7 +612,7 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
     for (int t = 0; t < tiles_per_item; ++t) {
       const int mt = p.pair ? 2 * unit + t : unit;
       const uint32_t slot = p.pair ? (uint32_t)t : set;
-      const uint32_t acc0 = lane_addr + (p.pair == kPairT ? slot : slot * 2) * acc_w, acc1 = acc0 + acc_w;
+      const uint32_t acc0 = lane_addr + (p.one_acc ? slot : slot * 2) * acc_w, acc1 = acc0 + acc_w;
       const long long m0 = (long long)mt * 128;
       const long long m = m0 + row;
       const int live_rows = mt < p.m_tiles ? (int)min((long long)128, p.m_limit - m0) : 0;
@@ -607,7 +641,7 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
         const uint32_t col = (uint32_t)g * 8 * P;
 #pragma unroll
         for (int i = 0; i < P; ++i) tmem_ld8p(acc0 + col + i * 8, r0 + 8 * i);
-        if (p.pair == kPairT) {
+        if (p.one_acc) {
 #pragma unroll
           for (int i = 0; i < 8 * P; ++i) r1[i] = 0;
         } else {
@@ -904,6 +938,96 @@ __device__ __forceinline__ void issuer_loop(const GenoMmaParams& p, int issuer, 
   LMDEC_WAITOUT(4, issuer == 2 && lane == 0);
 }
 
+
+// Round-robin issuers for data WITHOUT missing codes (one plane): issuer i owns the tile-chunks i, i + 4, ... of a work
+// item (a tile-chunk = one 128 x 256 block of one m-tile; pair mode streams tile 0 / tile 1 alternately) and issues all 8
+// K-blocks of them into ONE accumulator per tile.  Measured with the wait accounting (profiles/r02/waits_*.txt): with the
+// K-block-parity split each issuer made a full set of barrier round trips (~8 per chunk, ~100 cycles each) for only 4
+// MMAs and was busy 85 % of the time -- the issuers, not the tensor pipe (36 % busy) or the producers, paced the
+// no-missing shapes.  Whole tile-chunks halve the barrier work per MMA, four issuers overlap what is left, and the freed
+// accumulator columns deepen the decoded-operand ring (6 stages).
+// The first MMA of a tile overwrites its accumulator: the issuers that do not own the tile's first tile-chunk wait until
+// that one's operand stage has been released (= its MMAs are complete) before they add to the accumulator.
+// (A first version let one issuer run both tiles of a chunk: 16 MMAs and 3-5 tcgen05.commit in one burst hung on some
+// SMs, with the first commits never arriving; bursts of 8 MMAs + 2 commits, as everywhere else in this file, are fine.)
+template <int kTiles>
+__device__ __forceinline__ void issuer_loop_rr(const GenoMmaParams& p, int issuer, int lane, uint32_t tbase,
+                                               uint32_t bar0, uint32_t smem_b_a, int n_work, int chunks_per_split) {
+  const uint32_t empty_a = bar0 + 8 * kBarEmptyA, full_a = bar0 + 8 * kBarFullA;
+  const uint32_t full_b = bar0 + 8 * kBarFullB, empty_b = bar0 + 8 * kBarEmptyB;
+  const uint32_t acc_full = bar0 + 8 * kBarAccFull, acc_empty = bar0 + 8 * kBarAccEmpty;
+  const int N = p.N;
+  const uint32_t img_bytes = (uint32_t)kKbPerChunk * N * 32;
+  const uint32_t stage_bytes = img_bytes * p.n_img;
+  const uint32_t acc_w = N <= 64 ? 64 : 128;
+  const int acc_sets = p.acc_sets;
+  const uint32_t a_stages = (uint32_t)p.a_stages, b_stages = (uint32_t)p.b_stages;
+  const uint32_t idesc = make_idesc_i8(128, (uint32_t)N, 0, 1);
+  const uint64_t bdesc_ring = make_smem_desc(smem_b_a, (uint32_t)N * 16, 128);
+  const uint32_t a_ring = tbase + (uint32_t)p.a_ring_col0;
+  const uint32_t kb_step = (uint32_t)(2 * N);
+  LMDEC_WAITDECL;
+  uint32_t a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
+  uint32_t tile_no = 0;
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_no) {
+    const int sp = w / p.m_units;
+    const int c0 = sp * chunks_per_split;
+    const int c1 = min(c0 + chunks_per_split, p.n_chunks);
+    const uint32_t set = kTiles == 2 ? 0u : tile_no % acc_sets;
+    const uint32_t set_phase = kTiles == 2 ? (tile_no & 1) : ((tile_no / acc_sets) & 1);
+    LMDEC_WAITACC(1, issuer == 0 && lane == 0, mbar_wait_a(acc_empty + 8 * set, set_phase ^ 1));
+    tc_fence_after_sync();
+    const uint32_t first_stage = a_stage, first_phase = a_phase;   // ring position of the item's first tile-chunk
+    bool ordered = issuer < kTiles;      // issuer t owns the first tile-chunk of tile t
+    uint32_t tc = 0;                     // tile-chunk index within the work item
+    for (int c = c0; c < c1; ++c) {
+#pragma unroll
+      for (int t = 0; t < kTiles; ++t, ++tc) {
+        if ((tc & 3) == (uint32_t)issuer) {
+          LMDEC_WAITACC(2, issuer == 0 && lane == 0, mbar_wait_a(full_b + 8 * b_stage, b_phase));
+          const uint64_t bdesc0 = bdesc_ring + (uint64_t)((b_stage * stage_bytes) >> 4);
+          LMDEC_WAITACC(3, issuer == 0 && lane == 0, mbar_wait_a(full_a + 8 * a_stage, a_phase));
+          tc_fence_after_sync();
+          const uint32_t d_addr = tbase + (set * kTiles + t) * acc_w;
+          const uint32_t a_addr = a_ring + a_stage * 64;
+          if (!ordered) {
+            uint32_t fs = first_stage + t, fp = first_phase;
+            if (fs >= a_stages) {
+              fs -= a_stages;
+              fp ^= 1;
+            }
+            LMDEC_WAITACC(4, issuer == 2 && lane == 0, mbar_wait_a(empty_a + 8 * fs, fp));
+            tc_fence_after_sync();
+            ordered = true;
+          }
+          if (elect_one()) {
+            umma_ts_i8(d_addr, a_addr, bdesc0, idesc, c == c0 ? 0u : 1u);   // (c == c0 only for the tile's first owner)
+#pragma unroll
+            for (int j = 1; j < kKbPerChunk; ++j) umma_ts_i8(d_addr, a_addr + j * 8, bdesc0 + j * kb_step, idesc, 1u);
+            umma_commit_a(empty_a + 8 * a_stage);
+            umma_commit_a(empty_b + 8 * b_stage);      // (count kTiles: one per tile-chunk that read this B stage)
+          }
+          __syncwarp();
+        }
+        if (++a_stage == a_stages) {
+          a_stage = 0;
+          a_phase ^= 1;
+        }
+      }
+      if (++b_stage == b_stages) {
+        b_stage = 0;
+        b_phase ^= 1;
+      }
+    }
+    if (elect_one()) umma_commit_a(acc_full + 8 * set);
+    __syncwarp();
+  }
+  LMDEC_WAITOUT(1, issuer == 0 && lane == 0);
+  LMDEC_WAITOUT(2, issuer == 0 && lane == 0);
+  LMDEC_WAITOUT(3, issuer == 0 && lane == 0);
+  LMDEC_WAITOUT(4, issuer == 2 && lane == 0);
+}
+
 template <int kGroups>
 __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaParams p) {
   constexpr int kGroupWarps = kProducerWarps / kGroups;   // producer warps per tile-chunk
@@ -933,7 +1057,8 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   // single tiles: two issuer pairs take alternate chunks, so the per-chunk barrier round trips of an issuing thread
   // (~900 cycles of waits and commits around ~400 of MMA issue, profiles/r01/pipeline_trace.txt) overlap
   const bool interleave = kIssuerWarps == 4 && !p.pair && p.issuer_groups == 2;
-  const int n_issuers = (quad || interleave) ? 4 : 2;
+  const int n_issuers = (quad || interleave || p.rr) ? 4 : 2;
+  const int tiles_per_item_init = p.pair ? 2 : 1;
   const uint32_t kARingCol0 = (uint32_t)p.a_ring_col0;
   const uint32_t a_stage_cols = p.has_missing ? 128 : 64;
   const int acc_sets = p.acc_sets;
@@ -955,11 +1080,11 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     }
     for (int i = 0; i < kMaxAStages; ++i) {
       mbar_init(&bars[kBarFullA + i], kGroupWarps);
-      mbar_init(&bars[kBarEmptyA + i], p.pair == kPairT ? 1 : 2);
+      mbar_init(&bars[kBarEmptyA + i], (p.pair == kPairT || p.rr) ? 1 : 2);
     }
     for (int i = 0; i < kMaxBStages; ++i) {
       mbar_init(&bars[kBarFullB + i], 1);
-      mbar_init(&bars[kBarEmptyB + i], quad ? 4 : 2);
+      mbar_init(&bars[kBarEmptyB + i], p.rr ? tiles_per_item_init : (quad ? 4 : 2));
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[kBarAccFull + i], n_issuers);
@@ -972,6 +1097,9 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tbase = tmem_base_s;
+#ifdef LMDEC_DEBUG_HANG
+  if (blockIdx.x == 0 && tid == 0) printf("bars@%u rr=%d pair=%d acc_sets=%d a_stages=%d b_stages=%d n_chunks=%d splits=%d m_units=%d\n", bar0, p.rr, p.pair, p.acc_sets, p.a_stages, p.b_stages, p.n_chunks, p.splits, p.m_units);
+#endif
 #ifdef LMDEC_TRACE
   if (blockIdx.x == 0 && tid == 0) g_wait[14] = clock64();
 #endif
@@ -1142,7 +1270,11 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
   issuer_loop<PAIR, MISS, ILV>(p, issuer, lane, tbase, bar0, smem_b_a, n_work, chunks_per_split)
       // one instance per schedule: the issuing thread is the serial bottleneck of the pipeline, every mode test left in
       // its per-chunk path costs throughput
-      if (p.pair == kPairM) LMDEC_ISSUE(kPairM, true, false);
+      if (p.rr) {
+        if (p.pair) issuer_loop_rr<2>(p, issuer, lane, tbase, bar0, smem_b_a, n_work, chunks_per_split);
+        else issuer_loop_rr<1>(p, issuer, lane, tbase, bar0, smem_b_a, n_work, chunks_per_split);
+      }
+      else if (p.pair == kPairM) LMDEC_ISSUE(kPairM, true, false);
       else if (p.pair == kPairE) LMDEC_ISSUE(kPairE, false, false);
       else if (p.pair == kPairT) LMDEC_ISSUE(kPairT, false, false);
       else if (p.b_resident) {

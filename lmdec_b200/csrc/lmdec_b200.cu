@@ -41,6 +41,7 @@ struct lmdec_ctx {
   int producer_groups_missing = 1;   // the same with missing data (needs a decoded-A ring of >= 3 stages to pay)
   int acc_sets = 0;          // accumulator sets of single-tile work items: 0 = choose, 1, 2
   int b_resident = 1;        // short unsplit contractions keep the whole operand image in shared memory
+  int rr = 1;                // no missing data: round-robin whole-chunk issuers, one accumulator per tile
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
 };
@@ -1319,17 +1320,20 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
   p.issuer_groups = ctx.issuer_groups;
   // TMEM budget (512 columns): accumulators first, the rest is the decoded-A ring.  Short contractions alternate two
   // accumulator sets so the epilogue overlaps the next tile; long ones (epilogue negligible) give the columns to a
-  // deeper A ring instead.
+  // deeper A ring instead.  Without missing data (N <= 64) the round-robin issuer schedule keeps ONE accumulator per
+  // tile (geno_mma.cuh, issuer_loop_rr).
+  p.rr = (!has_missing && N <= 64 && ctx.rr && kIssuerWarps == 4) ? 1 : 0;
+  p.one_acc = (p.pair == kPairT || p.rr) ? 1 : 0;
   {
     const int acc_w = N <= 64 ? 64 : 128;
     int acc_cols;
     if (p.pair) {
       p.acc_sets = 1;
-      acc_cols = (p.pair == kPairT ? 2 : 4) * acc_w;
+      acc_cols = (p.one_acc ? 2 : 4) * acc_w;
     } else {
       p.acc_sets = (N <= 64 && p.n_chunks < ctx.pair_min_chunks) ? 2 : 1;
       if (ctx.acc_sets == 1 || (ctx.acc_sets == 2 && N <= 64)) p.acc_sets = ctx.acc_sets;
-      acc_cols = p.acc_sets * 2 * acc_w;
+      acc_cols = p.acc_sets * (p.one_acc ? 1 : 2) * acc_w;
     }
     p.a_ring_col0 = acc_cols;
     p.a_stages = (512 - acc_cols) / (has_missing ? 128 : 64);
@@ -1404,7 +1408,7 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
   // two thirds of the kernel's L2 -> SM traffic, which at ~42 B/cycle/SM is what bounds it (profiles/r02).
   p.b_resident = 0;
   const size_t image_bytes = (size_t)p.n_chunks * stage_bytes;
-  if (ctx.b_resident && !p.pair && p.splits == 1 && image_bytes + scratch + 4 * (size_t)kTileBytes <= budget) {
+  if (ctx.b_resident && !p.rr && !p.pair && p.splits == 1 && image_bytes + scratch + 4 * (size_t)kTileBytes <= budget) {
     p.b_resident = 1;
     tile_stages = (int)((budget - scratch - image_bytes) / kTileBytes);
     if (tile_stages > kMaxTileStages) tile_stages = kMaxTileStages;
@@ -1756,6 +1760,14 @@ int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const in
 }
 
 // ---- CUDA-event timing of the dominant kernel (bench.py's roofline): events are recorded on the launching stream
+#ifdef LMDEC_DEBUG_HANG
+int lmdec_hang_read(unsigned* host_out) {   // [0] = count, then (block, warp, barrier address, parity) x 64
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host_out, g_hang_n, sizeof(unsigned));
+  cudaMemcpyFromSymbol(host_out + 4 + 256, g_prog, sizeof(unsigned) * 148 * 8);
+  return (int)cudaMemcpyFromSymbol(host_out + 4, g_hang, sizeof(uint4) * 64);
+}
+#endif
 #ifdef LMDEC_TRACE
 int lmdec_trace_read(long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 12 * kTraceChunks);
@@ -1798,6 +1810,7 @@ int lmdec_ctx_set(lmdec_ctx* ctx, int knob, int value) {
     case LMDEC_KNOB_PRODUCER_GROUPS_MISSING: ctx->producer_groups_missing = value == 2 ? 2 : 1; return 0;
     case LMDEC_KNOB_ACC_SETS: ctx->acc_sets = value == 1 || value == 2 ? value : 0; return 0;
     case LMDEC_KNOB_B_RESIDENT: ctx->b_resident = value != 0; return 0;
+    case LMDEC_KNOB_ROUND_ROBIN: ctx->rr = value != 0; return 0;
   }
   return fail("lmdec_ctx_set: unknown knob");
 }
@@ -1813,6 +1826,7 @@ int lmdec_ctx_get(const lmdec_ctx* ctx, int knob) {
     case LMDEC_KNOB_PRODUCER_GROUPS_MISSING: return c.producer_groups_missing;
     case LMDEC_KNOB_ACC_SETS: return c.acc_sets;
     case LMDEC_KNOB_B_RESIDENT: return c.b_resident;
+    case LMDEC_KNOB_ROUND_ROBIN: return c.rr;
   }
   return -1;
 }

@@ -3,9 +3,15 @@
 // follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor" tables.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_fp16.h>
 
 namespace lmdec {
+#ifdef LMDEC_DEBUG_HANG
+__device__ unsigned g_hang_n;
+__device__ unsigned g_prog[148 * 8];
+__device__ uint4 g_hang[64];
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // shared-memory address helpers
@@ -102,7 +108,16 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_a(bar, parity)) {
-    if (++spins > LMDEC_MBAR_SPIN_LIMIT) __trap();
+    if (++spins > LMDEC_MBAR_SPIN_LIMIT) {
+#ifdef LMDEC_DEBUG_HANG   // protocol debugging: record who waits on what and carry on (results are garbage, the kernel ends)
+      if ((threadIdx.x & 31) == 0 && threadIdx.x >= 512) {
+        const unsigned slot = atomicAdd(&g_hang_n, 1u);
+        if (slot < 64) g_hang[slot] = make_uint4(blockIdx.x, threadIdx.x >> 5, bar, parity);
+      }
+      return;
+#endif
+      __trap();
+    }
   }
 }
 // Waits that are off the critical path (epilogue warps waiting for a whole tile of MMAs, loaders waiting for a ring slot
@@ -116,7 +131,16 @@ __device__ __forceinline__ void mbar_wait_relaxed_a(uint32_t bar, uint32_t parit
   uint32_t spins = 0;
   while (!mbar_try_wait_a(bar, parity)) {
     __nanosleep(LMDEC_PARK_NS);
-    if (++spins > LMDEC_MBAR_SPIN_LIMIT) __trap();
+    if (++spins > LMDEC_MBAR_SPIN_LIMIT) {
+#ifdef LMDEC_DEBUG_HANG
+      if ((threadIdx.x & 31) == 0 && threadIdx.x >= 512) {
+        const unsigned slot = atomicAdd(&g_hang_n, 1u);
+        if (slot < 64) g_hang[slot] = make_uint4(blockIdx.x, threadIdx.x >> 5, bar, parity | 0x100u);
+      }
+      return;
+#endif
+      __trap();
+    }
   }
 #else
   mbar_wait_a(bar, parity);
@@ -183,6 +207,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
