@@ -416,7 +416,7 @@ def run_ours(args):
     launches = lib.lmdec_launch_count() - launches0
     kernel_events = store_mod.KERNEL_EVENTS
     store_mod.KERNEL_EVENTS = None
-    k_ms = {"dot": [], "tdot": []}          # whole operator application (stats + planes + product + finalize)
+    k_ms = {"dot": [], "tdot": [], "apass": []}   # whole operator application (stats + planes + product + finalize)
     for tag, a, b in kernel_events:
         k_ms[tag].append(a.elapsed_time(b))
     mma_total_ms, mma_launches = store.ctx.timing_read()
@@ -515,6 +515,7 @@ def run_ours(args):
                          "kernel_share_of_step": mma_total_ms / ms_total,
                          "operator_dot_ms": float(np.mean(k_ms["dot"])) if k_ms["dot"] else None,
                          "operator_tdot_ms": float(np.mean(k_ms["tdot"])) if k_ms["tdot"] else None,
+                         "operator_apass_ms": float(np.mean(k_ms["apass"])) if k_ms["apass"] else None,
                          "algorithmic_flops_per_launch": flops_launch,
                          "algorithmic_bytes_per_launch": N_ROWS * N_COLS / 4,
                          "t_tensor_ms": t_tensor * 1e3, "t_hbm_ms": t_hbm * 1e3, "peak_source": pk["source"]},

@@ -178,6 +178,22 @@ int lmdec_operator_apply(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_
                          int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, void* out, int64_t ldo,
                          void* stream);
 
+/* The whole step of the power iteration in ONE call (SURVEY 8b `lmdec_apass`): the Gram operator applied to an
+ * orthonormal block,   t = A^T q  (p x K float32, kept: V and the v-subspace / rmse metrics reuse it)   and
+ * x = A t * inv_factor  (n_limit x K float64) -- `x = A.dot(A.T.dot(q)) / factor` of PowerMethod._solution_step
+ * (lmdec/decomp/iter_methods.py:383-385; legacy: ScaledCenterArray.sym_mat_mult, scaled_legacy.py:379-399).
+ * Both orientations of the store are passed (sample-major n x p for A t, SNP-major p x n for A^T q); n_limit <= n is the
+ * row prefix in use (SuccessiveBatchedPowerMethod).  q_flags: bit 0 = q's column statistics are already in `work` (left
+ * by lmdec_cholqr2_small / _grid), bit 1 = q is float32.  Scratch as for lmdec_operator_apply; image_q holds
+ * lmdec_image_bytes(n, N), image1 / image2 lmdec_image_bytes(p, N).  Everything is enqueued on `stream`, nothing
+ * returns to the host in between.  (A is still read twice per step, once per orientation: with 3 int8 planes and an
+ * indicator plane the step is bound by the tensor-core / decode work, not by the 2 x n p / 4 bytes -- DESIGN.md 3.) */
+int lmdec_apass(lmdec_ctx* ctx, const uint8_t* sample_store, const uint8_t* snp_store, int64_t n, int64_t p,
+                int64_t n_limit, int has_missing, const void* q, int64_t ldq, int q_flags, int K, int P,
+                const double* scale, const double* impute, const double* center_w, double* work, int8_t* image_q,
+                int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, float* t_out, double* x_out, int64_t ldx,
+                double inv_factor, void* stream);
+
 /* K x K Cholesky whitening on the device (one block, float64): G = r^T r, r upper triangular, r_inv = r^-1.
  * *flag (int32, device) = 1 when G is not numerically positive definite (pivot of the unit-diagonal-scaled matrix below
  * rank_tol, or non-finite input): the host then takes its rank-revealing path.  The K x K step of CholeskyQR2, in

@@ -1623,6 +1623,41 @@ int lmdec_operator_apply(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_
   return rc;
 }
 
+__global__ void scale_inplace_kernel(double* __restrict__ x, int64_t m, int K, int64_t ld, double a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m * K) x[(i / K) * ld + i % K] *= a;
+}
+
+// One application of the Gram operator, the whole step of the power iteration (lmdec/decomp/iter_methods.py:383-385):
+//   t = A^T q  (p x K, float32)      x = A t * inv_factor  (n_limit x K, float64)
+// Two passes over the two orientations of the store, every kernel of both enqueued by this one call: operand statistics
+// of q (skipped with flag 1), planes of q, A^T q with the statistics of t reduced in its epilogue, planes of t, A t with
+// the diagonal / rank-1 terms in its epilogue, the division by the factor.
+int lmdec_apass(lmdec_ctx* ctx, const uint8_t* sample_store, const uint8_t* snp_store, int64_t n, int64_t p,
+                int64_t n_limit, int has_missing, const void* q, int64_t ldq, int q_flags, int K, int P,
+                const double* scale, const double* impute, const double* center_w, double* work, int8_t* image_q,
+                int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, float* t_out, double* x_out, int64_t ldx,
+                double inv_factor, void* stream) {
+  if (!sample_store || !snp_store || !q || !t_out || !x_out) return fail("lmdec_apass: null operand");
+  if (n_limit <= 0 || n_limit > n) return fail("lmdec_apass: bad row limit");
+  const int q_f32 = (q_flags & 2) ? 4 : 0;
+  const int q_ready = (q_flags & 1) ? 32 : 0;
+  // A^T q: transpose (1) | float32 out (8) | leave the statistics of t in work (16)
+  int rc = lmdec_operator_apply(ctx, snp_store, p, n, p, n_limit, has_missing, 1 | 8 | 16 | q_f32 | q_ready, q, ldq, K, P,
+                                scale, impute, center_w, work, image_q, nullptr, acc0, acc1, t_out, K, stream);
+  if (rc) return rc;
+  // A t: float32 operand (4) | its statistics are in work (32)
+  rc = lmdec_operator_apply(ctx, sample_store, n, p, n_limit, p, has_missing, 4 | 32, t_out, K, K, P, scale, impute,
+                            center_w, work, image1, image2, acc0, acc1, x_out, ldx, stream);
+  if (rc) return rc;
+  if (inv_factor != 1.0) {
+    scale_inplace_kernel<<<(unsigned)cdiv(n_limit * K, 256), 256, 0, (cudaStream_t)stream>>>(x_out, n_limit, K, ldx,
+                                                                                           inv_factor);
+    rc = check_launch("lmdec_apass (factor)");
+  }
+  return rc;
+}
+
 int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, double* r, int* flag, void* stream) {
   if (K < 1 || K > 128) return fail("lmdec_chol_whiten: K out of range (1..128)");
   const size_t smem = (size_t)(2 * K * K + K) * sizeof(double);

@@ -271,7 +271,13 @@ class PowerMethod(_IterAlgo):
 
     def _next(self, st):
         if "next_raw" not in st:
-            st["next_raw"] = self.array.dot_t(self._t(st))   # A A^T q, before the factor
+            fused = None
+            if "t" not in st and hasattr(self.array, "apass_t"):
+                fused = self.array.apass_t(st["q"])          # one C call: t = A^T q and A t (lmdec_apass)
+            if fused is not None:
+                st["t"], st["next_raw"] = fused
+            else:
+                st["next_raw"] = self.array.dot_t(self._t(st))   # A A^T q, before the factor
         return st["next_raw"]
 
     def _wrap_input(self, data):

@@ -448,6 +448,39 @@ class GenotypeOperator:
     def qr_stats_emitted(self, q: torch.Tensor):
         self._buffers(q.shape[1])["emitted"] = ("q", weakref.ref(q), q._version)
 
+    def apass_t(self, q: torch.Tensor, inv_factor: float = 1.0):
+        """(t, x) = (A^T q, A t * inv_factor) in ONE C call (`lmdec_apass`): the step of the power iteration.
+        Returns None when this operator cannot take the fused call (row-sharded samples, a row-range view, wide K)."""
+        st, lib = self.store, self.store.lib
+        if st.group is not None or q.ndim != 2 or q.shape[0] != self.rows or q.shape[1] > self._max_cols() \
+                or self.rows == 0 or q.dtype not in (F64, torch.float32) or not _FUSED_STATS:
+            return None
+        if q.stride(1) != 1 or q.stride(0) != q.shape[1]:
+            q = q.contiguous()
+        K = q.shape[1]
+        buf = self._buffers(K)
+        emitted = buf.pop("emitted", None)
+        q_flags = 2 if q.dtype == torch.float32 else 0
+        if emitted is not None:
+            kind, ref, version = emitted
+            if kind == "q" and ref() is q and q._version == version:
+                q_flags |= 1              # the orthonormalisation kernel left q's column statistics in the work buffer
+        t = torch.empty((st.p, K), dtype=torch.float32, device=st.device)
+        x = torch.empty((self.rows, K), dtype=F64, device=st.device)
+        miss = self.has_missing
+        with _timed("apass"):
+            _capi.check(lib.lmdec_apass(
+                st.ctx.handle, _capi.ptr(st.s_store), _capi.ptr(st.v_store), st.n, st.p, self.rows, int(miss),
+                _capi.ptr(q), K, q_flags, K, self.planes, _capi.ptr(self.inv_std),
+                _capi.ptr(self.impute_mean) if miss else None, _capi.ptr(self._center_w()),
+                _capi.ptr(buf["work"]), _capi.ptr(buf["im1"]), _capi.ptr(buf["im1"]), _capi.ptr(buf["im2"]),
+                _capi.ptr(buf["acc0"]), _capi.ptr(buf["acc1"]), _capi.ptr(t), _capi.ptr(x), K, float(inv_factor),
+                _capi.stream_ptr()), "lmdec_apass")
+        if st.snp_group is not None:      # SNP shards: the n x K partial products are the only exchange
+            import torch.distributed as dist
+            dist.all_reduce(x, group=st.snp_group)
+        return t, x
+
     def dot_t(self, t: torch.Tensor) -> torch.Tensor:
         """x[n_local, K] = A t  for t [p, K] float64 on the device."""
         squeeze = t.ndim == 1
