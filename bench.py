@@ -296,6 +296,7 @@ def run_target(torch, dist, device, world, rank, group, planes):
     ms_iter = float(ms.item())
     # ---- oracle check on the first `slab` SNPs: gather U (n x k) and the decoded slab (n x slab) on rank 0
     u_loc = U.t.contiguous()
+    w_prod = op.tdot_t(u_loc, out_dtype=torch.float64)[:slab].cpu().numpy()     # (A^T U)[J] through the product path
     codes = store.to_dense(transpose=True, rows=slab).T.contiguous()            # [n_loc, slab] int8
     if world > 1:
         sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
@@ -322,6 +323,7 @@ def run_target(torch, dist, device, world, rank, group, planes):
         pk = peaks()
         t_roof = max(flops_iter / world / (pk["tensor_tflops"] * 1e12), (n / world) * p / 4 / (pk["hbm_gbs"] * 1e9))
         col_err = np.linalg.norm(w_ref - w_gpu * sign, axis=0) / np.linalg.norm(w_ref, axis=0)
+        prod_err = float(np.max(np.abs(w_prod - w_ref)) / np.max(np.abs(w_ref)))
         out = {"problem": "top-10 PCA of a 100,000 x 500,000 2-bit genotype matrix (6 synthetic populations, no "
                           "missing codes), centre + binom scale, K = 20, q-vals tol 1e-4, x0 = default_rng(42)",
                "parallelism": "single GPU" if world == 1 else
@@ -332,7 +334,12 @@ def run_target(torch, dist, device, world, rank, group, planes):
                "ms_per_iteration": ms_iter, "tflops": flops_iter / (ms_iter * 1e-3) / 1e12,
                "roofline_frac_per_gpu": t_roof / (ms_iter * 1e-3), "store_build_seconds": t_build,
                "S": [float(v) for v in S_np],
-               "oracle_slab_check": {"slab_snps": slab, "rel_err_AtU_vs_V_S_sqrt_n": err,
+               "oracle_slab_check": {"slab_snps": slab,
+                                     # parity of the product itself at full size (oracle float64 vs the tensor-core path)
+                                     "max_err_AtU_product_vs_oracle": prod_err,
+                                     # SVD identity A^T U = V S sqrt(n): holds per component once that component has
+                                     # converged (the separated population components; the bulk ones are still rotating)
+                                     "rel_err_AtU_vs_V_S_sqrt_n": err,
                                      "rel_err_per_component": [float(v) for v in col_err],
                                      "S_from_oracle_slab_rel_dev": float(np.max(np.abs(s_slab - S_np) / S_np))}}
     del op, store
@@ -359,6 +366,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
         group = dist.group.WORLD
     lib = _capi.load()
+    if args.target_only:
+        target = run_target(torch, dist, device, world, rank, group, args.planes)
+        if rank == 0:
+            print(json.dumps({"target": target, "env": {k: v for k, v in os.environ.items() if k.startswith("LMDEC_")}}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     K = K_TOP + BUFFER
     by_rows = resolve_shard(args.shard) == "rows" and world > 1
     n_global = N_ROWS * world if by_rows else N_ROWS
@@ -460,14 +474,22 @@ def run_ours(args):
     # ---- time-to-converged SVD through PowerMethod.svd (informative; BASELINE metric's first half)
     svd_info = None
     if rank == 0 or world > 1:
-        pm2 = PowerMethod(k=K_TOP, buffer=BUFFER, tol=1e-4, scoring_method="q-vals", sub_svd_start=False, lmbd=0,
-                          max_iter=100)
+        kw2 = dict(k=K_TOP, buffer=BUFFER, tol=1e-4, scoring_method="q-vals", sub_svd_start=False, lmbd=0)
+        # first call: pays the lazy loading of every kernel svd() touches for the first time (finalization: cuBLAS
+        # float64 GEMMs, the large-iterate QR) -- reported, then the same call again is the time-to-converged
+        barrier()
+        ts = time.time()
+        PowerMethod(max_iter=3, **kw2).svd(op, x0=x0_full[my_rows], verbose=False)
+        torch.cuda.synchronize()
+        t_first = time.time() - ts
+        pm2 = PowerMethod(max_iter=100, **kw2)
         barrier()
         ts = time.time()
         pm2.svd(op, x0=x0_full[my_rows], verbose=False)
         torch.cuda.synchronize()
         svd_info = {"seconds": time.time() - ts, "iterations": pm2.num_iter, "tol": 1e-4,
-                    "store_build_seconds": t_build}
+                    "ms_per_iteration": (time.time() - ts) * 1e3 / max(pm2.num_iter, 1),
+                    "first_call_3_iterations_seconds": t_first, "store_build_seconds": t_build}
 
     # ---- the north-star problem (strong scaling over the N GPUs): see run_target
     target = None
@@ -542,6 +564,7 @@ def main():
                     help="multi-GPU decomposition: by shape (auto: SNP shards for this n << p workload), or forced")
     ap.add_argument("--no-target", dest="target", action="store_false",
                     help="skip the north-star problem (100k x 500k, row-sharded, run to convergence)")
+    ap.add_argument("--target-only", action="store_true", help="run only the north-star problem (key `target`)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps")
     args = ap.parse_args()

@@ -38,7 +38,10 @@ namespace lmdec {
 // missing data (deep A ring: 61,000 x 800,000 K=30 -7 %); with missing data the ring has two stages, each group would
 // own one and serialise with its MMAs (+17 % on A t), so one group is used there.  (A run-time switch inside one
 // kernel cost 6 %: the producer loop is that sensitive to extra instructions.)
-constexpr int kProducerWarps = 8;
+#ifndef LMDEC_PRODUCER_WARPS
+#define LMDEC_PRODUCER_WARPS 8
+#endif
+constexpr int kProducerWarps = LMDEC_PRODUCER_WARPS;          // 8, or 16 (more decode warps in flight per scheduler)
 #ifndef LMDEC_ISSUER_WARPS
 #define LMDEC_ISSUER_WARPS 4
 #endif
@@ -1128,7 +1131,7 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       const int c1 = min(c0 + chunks_per_split, p.n_chunks);
       // in pair mode the tile stream alternates between the two m-tiles of the work item, chunk by chunk
       for (int sc = (c1 - c0) * tiles_per_item; sc > 0; --sc, ++gsc) {
-        if (kGroups == 2 && (gsc & 1) != (uint32_t)group) {   // the other group's tile-chunk: step the ring positions
+        if (kGroups > 1 && (gsc % (uint32_t)kGroups) != (uint32_t)group) {   // the other group's tile-chunk: step the ring positions
           if (++a_stage == (uint32_t)a_stages) {
             a_stage = 0;
             a_phase ^= 1;

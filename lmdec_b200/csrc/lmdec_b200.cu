@@ -1430,6 +1430,9 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
     cudaError_t e = cudaFuncSetAttribute(geno_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(geno_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(geno_mma_kernel<(kProducerWarps >= 16 ? 4 : 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               223 * 1024);
     if (e != cudaSuccess) return fail("lmdec_geno_matmul: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -1447,7 +1450,15 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
     cudaEventRecord(ev0, st);
   }
   // producer grouping (see geno_mma.cuh): two groups without missing data, one with
-  if (has_missing ? (ctx.producer_groups_missing == 2 && p.a_stages >= 3) : ctx.producer_groups == 2)
+  int groups = has_missing ? ctx.producer_groups_missing : ctx.producer_groups;
+#ifndef LMDEC_GROUPS_ANY_STAGES
+  if (has_missing && p.a_stages < 3) groups = 1;
+#endif
+  if (groups > p.a_stages) groups = p.a_stages >= 2 ? 2 : 1;   // a group owns at least one stage of the decoded-A ring
+  if (groups == 4 && kProducerWarps < 16) groups = 2;
+  if (groups == 4)
+    geno_mma_kernel<(kProducerWarps >= 16 ? 4 : 2)><<<grid, kThreads, smem, st>>>(p);
+  else if (groups == 2)
     geno_mma_kernel<2><<<grid, kThreads, smem, st>>>(p);
   else
     geno_mma_kernel<1><<<grid, kThreads, smem, st>>>(p);
@@ -1841,8 +1852,8 @@ int lmdec_ctx_set(lmdec_ctx* ctx, int knob, int value) {
     case LMDEC_KNOB_PAIR_MODE: ctx->pair_mode = value != 0; return 0;
     case LMDEC_KNOB_PAIR_MIN_CHUNKS: ctx->pair_min_chunks = value < 2 ? 2 : value; return 0;
     case LMDEC_KNOB_ISSUER_GROUPS: ctx->issuer_groups = value == 1 ? 1 : 2; return 0;
-    case LMDEC_KNOB_PRODUCER_GROUPS: ctx->producer_groups = value == 1 ? 1 : 2; return 0;
-    case LMDEC_KNOB_PRODUCER_GROUPS_MISSING: ctx->producer_groups_missing = value == 2 ? 2 : 1; return 0;
+    case LMDEC_KNOB_PRODUCER_GROUPS: ctx->producer_groups = value == 1 ? 1 : (value == 4 ? 4 : 2); return 0;
+    case LMDEC_KNOB_PRODUCER_GROUPS_MISSING: ctx->producer_groups_missing = value == 2 ? 2 : (value == 4 ? 4 : 1); return 0;
     case LMDEC_KNOB_ACC_SETS: ctx->acc_sets = value == 1 || value == 2 ? value : 0; return 0;
     case LMDEC_KNOB_B_RESIDENT: ctx->b_resident = value != 0; return 0;
     case LMDEC_KNOB_ROUND_ROBIN: ctx->rr = value != 0; return 0;
