@@ -224,6 +224,30 @@ int lmdec_cholqr2_grid(const double* X, int64_t ldx, int64_t n, int K, double ra
 int lmdec_qr_pack(const double* r1, const double* r2, const double* g2, const int* flag1, const int* flag2, int K,
                   double* packed, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Dense float operands: the member products of `ChainedArray.dot` / `.T.dot` for dense float matrices
+ * (lmdec/array/chained.py:169-177, 159-167 -> dask chunk matmuls `np.dot(chunk, x)`; BASELINE configs[4]).
+ * The matrix lives in HBM as float32 in a pre-tiled store (tiles of 128 rows x 32 contraction elements, 16 KB, one
+ * bulk copy each); one store per orientation, as for genotypes.  The product runs on the tensor cores as
+ * error-compensated TF32 (A_hi B_hi + A_lo B_hi + A_hi B_lo, float32 accumulation): float32-level accuracy.
+ * ------------------------------------------------------------------------------------------------------------- */
+int64_t lmdec_dense_store_bytes(int64_t M, int64_t Kd);
+int64_t lmdec_dense_image_bytes(int64_t Kd, int N);            /* N = 16 * ceil(K / 16); one image (hi or lo) */
+/* src: row-major [rows, cols] (leading dimension ld, elements), dtype 0 = float32, 1 = float64 (rounded to float32).
+ * transpose = 0: store of src (M = rows, contraction = cols); 1: store of src^T (M = cols, contraction = rows). */
+int lmdec_dense_pack(const void* src, int dtype, int64_t rows, int64_t cols, int64_t ld, int transpose, float* store,
+                     void* stream);
+int lmdec_dense_unpack(const float* store, int64_t M, int64_t Kd, float* dst, int64_t ld, void* stream);
+/* out[m_limit, K] (float64, leading dimension ldo) = store[0:m_limit, 0:kd_limit] * B[0:kd_limit, 0:K].
+ * B: row-major, leading dimension ldb, b_dtype 0 = float32, 1 = float64; K <= 128 columns per call.
+ * image_hi / image_lo: scratch of lmdec_dense_image_bytes(kd_limit, N) bytes each.  splits = 0: chosen by the library
+ * (contraction ranges accumulate with float64 atomicAdd into the zeroed output).  Row prefixes (m_limit, kd_limit) are
+ * the `array[0:m, :]` views of SuccessiveBatchedPowerMethod (iter_methods.py:557,573). */
+int lmdec_dense_matmul(lmdec_ctx* ctx, const float* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
+                       const void* B, int b_dtype, int64_t ldb, int K, float* image_hi, float* image_lo, double* out,
+                       int64_t ldo, int splits, void* stream);
+
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblmdec_b200.so")
 SOURCES = [os.path.join(CSRC, "lmdec_b200.cu")]
-HEADERS = [os.path.join(CSRC, "geno_mma.cuh"), os.path.join(CSRC, "umma.cuh"),
+HEADERS = [os.path.join(CSRC, "geno_mma.cuh"), os.path.join(CSRC, "dense_mma.cuh"), os.path.join(CSRC, "umma.cuh"),
            os.path.join(HERE, "..", "include", "lmdec_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

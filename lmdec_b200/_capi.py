@@ -55,6 +55,11 @@ SIGNATURES = {
     "lmdec_ctx_timing": (None, [_p, _i32]),
     "lmdec_ctx_timing_read": (_i32, [_p, _p, _p]),
     "lmdec_sqdiff": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p]),
+    "lmdec_dense_store_bytes": (_i64, [_i64, _i64]),
+    "lmdec_dense_image_bytes": (_i64, [_i64, _i32]),
+    "lmdec_dense_pack": (_i32, [_p, _i32, _i64, _i64, _i64, _i32, _p, _p]),
+    "lmdec_dense_unpack": (_i32, [_p, _i64, _i64, _p, _i64, _p]),
+    "lmdec_dense_matmul": (_i32, [_p, _p, _i64, _i64, _i64, _i64, _p, _i32, _i64, _i32, _p, _p, _p, _i64, _i32, _p]),
 }
 
 

@@ -14,11 +14,78 @@ import torch
 from ..device import F64, DeviceArray, as_tensor, require_cuda
 
 
+class DenseTiles:
+    """float32 tile stores of a dense [n, p] matrix (one per orientation, built on first use) and the tcgen05 product
+    over them (`lmdec_dense_matmul`, csrc/dense_mma.cuh): error-compensated TF32, float32-level accuracy.
+
+    The reference multiplies dense members chunk by chunk with `np.dot` (lmdec/array/chained.py:169-177); here the
+    matrix is streamed once per product at HBM speed.  Like the genotype store it keeps both orientations, so `A.dot`
+    and `A.T.dot` are the same kernel ("rows of a store times a narrow operand")."""
+
+    def __init__(self, a: torch.Tensor):
+        from .. import _capi
+        self._capi = _capi
+        self.lib = _capi.load()
+        self.ctx = _capi.Context()
+        self.a = a                      # [n, p] float32, row-major, on the device
+        self.n, self.p = a.shape
+        self._stores = {}
+        self._img = {}
+
+    def store(self, transpose: bool) -> torch.Tensor:
+        st = self._stores.get(transpose)
+        if st is None:
+            M, Kd = (self.p, self.n) if transpose else (self.n, self.p)
+            st = torch.empty(self.lib.lmdec_dense_store_bytes(M, Kd) // 4, dtype=torch.float32, device=self.a.device)
+            self._capi.check(self.lib.lmdec_dense_pack(self._capi.ptr(self.a), 0, self.n, self.p, self.a.stride(0),
+                                                       int(transpose), self._capi.ptr(st), self._capi.stream_ptr()),
+                             "lmdec_dense_pack")
+            self._stores[transpose] = st
+        return st
+
+    def matmul(self, b: torch.Tensor, transpose: bool, rows: int) -> torch.Tensor:
+        """A[0:rows] b (transpose = False, b [p, K]) or A[0:rows]^T b (transpose = True, b [rows, K]); float64 out."""
+        capi, lib = self._capi, self.lib
+        if b.dtype not in (F64, torch.float32):
+            b = b.to(F64)
+        if b.stride(1) != 1:
+            b = b.contiguous()
+        M, Kd = (self.p, self.n) if transpose else (self.n, self.p)
+        m_limit, kd_limit = (self.p, rows) if transpose else (rows, self.p)
+        K = b.shape[1]
+        out = torch.empty((m_limit, K), dtype=F64, device=b.device)
+        if m_limit == 0 or K == 0:
+            return out
+        if kd_limit == 0:
+            return out.zero_()
+        st = self.store(transpose)
+        for k0 in range(0, K, 128):             # one tensor-core N tile (<= 128 operand columns) per launch
+            kb = min(128, K - k0)
+            N = (kb + 15) // 16 * 16
+            key = (transpose, N)
+            img = self._img.get(key)
+            if img is None:
+                nb = lib.lmdec_dense_image_bytes(Kd, N) // 4
+                img = self._img[key] = (torch.empty(nb, dtype=torch.float32, device=b.device),
+                                        torch.empty(nb, dtype=torch.float32, device=b.device))
+            bk, ok = b[:, k0:k0 + kb], out[:, k0:k0 + kb]
+            capi.check(lib.lmdec_dense_matmul(
+                self.ctx.handle, capi.ptr(st), M, Kd, m_limit, kd_limit, capi.ptr(bk), int(b.dtype == F64),
+                b.stride(0), kb, capi.ptr(img[0]), capi.ptr(img[1]), capi.ptr(ok), out.stride(0), 0,
+                capi.stream_ptr()), "lmdec_dense_matmul")
+        return out
+
+
 class DenseOperator:
-    """A [n, p] floating matrix resident in HBM."""
+    """A [n, p] floating matrix resident in HBM.
+
+    float32 matrices of at least `native_min_elems` elements multiply through `DenseTiles` (hand-written tcgen05
+    kernel); float64 matrices and small ones are plain library GEMMs."""
 
     ndim = 2
     group = None
+    native_min_elems = int(os.environ.get("LMDEC_DENSE_NATIVE_MIN", str(1 << 22)))   # below: not worth two tile stores
+    native = os.environ.get("LMDEC_DENSE_NATIVE", "1") != "0"
 
     def __init__(self, a, device=None, keep_dtype: bool = False):
         device = device or require_cuda()
@@ -36,6 +103,41 @@ class DenseOperator:
         if t.ndim != 2:
             raise ValueError("expected a 2-D array")
         self.a = t
+        self._init_views()
+
+    def _init_views(self, root=None, rows=None, transposed=False):
+        self._root = root                # the operator that owns the tile stores (None: this one)
+        self._rows = rows                # row prefix of the root this view covers (None: all)
+        self._transposed = transposed    # this view is root[0:rows].T
+        self._tiles = None
+
+    def _view(self, a, rows=None, transposed=False):
+        out = DenseOperator.__new__(DenseOperator)
+        out.a = a
+        out._init_views(self._root or self, rows if rows is not None else self._rows, transposed)
+        return out
+
+    def _plain(self, a):
+        out = DenseOperator.__new__(DenseOperator)
+        out.a = a
+        out._init_views()
+        return out
+
+    def _native_tiles(self):
+        """DenseTiles of the root matrix when this view can use the tensor-core path, else None"""
+        root = self._root or self
+        a = root.a
+        if not (DenseOperator.native and a.is_cuda and a.dtype == torch.float32 and a.ndim == 2
+                and a.numel() >= DenseOperator.native_min_elems and a.stride(1) == 1):
+            return None
+        if root._tiles is None:
+            root._tiles = DenseTiles(a)
+        return root._tiles
+
+    @property
+    def path(self) -> str:
+        """'tcgen05' or 'cublas': which product path this operator takes (tests assert on it)"""
+        return "tcgen05" if self._native_tiles() is not None else "cublas"
 
     @property
     def shape(self):
@@ -47,14 +149,10 @@ class DenseOperator:
 
     @property
     def T(self):
-        out = DenseOperator.__new__(DenseOperator)
-        out.a = self.a.T
-        return out
+        return self._view(self.a.T, transposed=not self._transposed)
 
-    # float32 matrices: "fp32" (default) = plain fp32 library GEMM; "tf32x3" = error-compensated split
-    # A = A_hi + A_lo, x = x_hi + x_lo on the TF32 tensor cores (A_hi x_hi + A_lo x_hi + A_hi x_lo: fp32-level accuracy).
-    # Measured on configs[4] (1M x 4k, K = 110) the three skinny cuBLAS TF32 GEMMs are slower than the fp32 one (58 vs
-    # 47 ms per iteration), so it stays opt-in until the dense path gets its own tcgen05 kernel.
+    # float32 matrices below the native threshold: "fp32" (default) = plain fp32 library GEMM; "tf32x3" = the same
+    # error-compensated split on cuBLAS TF32 GEMMs (A/B reference for the tcgen05 kernel; slower than fp32 on cuBLAS).
     f32_mode = os.environ.get("LMDEC_DENSE_F32", "fp32")
 
     def _split(self):
@@ -82,19 +180,31 @@ class DenseOperator:
             torch.backends.cuda.matmul.allow_tf32 = prev
         return out
 
+    def _product(self, x, transpose: bool):
+        """this view times x (transpose: its transpose times x)"""
+        squeeze = x.ndim == 1
+        if squeeze:
+            x = x[:, None]
+        tiles = self._native_tiles()
+        if tiles is not None:
+            rows = tiles.n if self._rows is None else self._rows
+            out = tiles.matmul(x, transpose != self._transposed, rows)
+        elif self.a.dtype == torch.float32:
+            out = self._mm32(x, transpose)
+        else:
+            a = self.a.T if transpose else self.a
+            out = (a @ x.to(self.a.dtype)).to(F64)
+        return out[:, 0] if squeeze else out
+
     def dot_t(self, x):
         if x.shape[0] != self.a.shape[1]:
             raise ValueError("shapes {} and {} not aligned".format(self.shape, tuple(x.shape)))
-        if self.a.dtype == torch.float32:
-            return self._mm32(x, False)
-        return (self.a @ x.to(self.a.dtype)).to(F64)
+        return self._product(x, False)
 
     def tdot_t(self, y):
         if y.shape[0] != self.a.shape[0]:
             raise ValueError("shapes {} and {} not aligned".format(self.shape[::-1], tuple(y.shape)))
-        if self.a.dtype == torch.float32:
-            return self._mm32(y, True)
-        return (self.a.T @ y.to(self.a.dtype)).to(F64)
+        return self._product(y, True)
 
     def dot(self, x):
         return DeviceArray(self.dot_t(as_tensor(x, self.a.device)))
@@ -105,9 +215,20 @@ class DenseOperator:
         elif isinstance(item, np.ndarray):
             item = torch.as_tensor(item, device=self.a.device)
         sub = self.a[item]
-        out = DenseOperator.__new__(DenseOperator)
-        out.a = sub if sub.ndim == 2 else sub.reshape(1, -1)
-        return out
+        sub = sub if sub.ndim == 2 else sub.reshape(1, -1)
+        # a row prefix [0:m, :] of an untransposed matrix stays a view of the same tile stores (the cumulative
+        # partitions of SuccessiveBatchedPowerMethod, iter_methods.py:557,573); anything else is a new plain matrix
+        rows = None
+        if isinstance(item, slice):
+            rows = item
+        elif isinstance(item, tuple) and len(item) == 2 and isinstance(item[0], slice) \
+                and isinstance(item[1], slice) and item[1] == slice(None):
+            rows = item[0]
+        if rows is not None and not self._transposed:
+            start, stop, step = rows.indices(self.a.shape[0])
+            if start == 0 and step == 1:
+                return self._view(sub, rows=stop)
+        return self._plain(sub)
 
     def to_dense(self):
         return self.a.to(F64)

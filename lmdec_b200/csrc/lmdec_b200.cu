@@ -10,6 +10,7 @@
 #include <utility>
 #include "../../include/lmdec_b200.h"
 #include "geno_mma.cuh"
+#include "dense_mma.cuh"
 
 namespace {
 thread_local char g_err[512] = "";
@@ -1894,6 +1895,127 @@ int lmdec_ctx_timing_read(lmdec_ctx* ctx, double* total_ms, int64_t* launches) {
   *total_ms = tot;
   *launches = (int64_t)ctx->events.size();
   return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dense float32 operands (dense_mma.cuh): tile store, TF32 hi / lo operand images, the 3xTF32 tcgen05 product
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int64_t lmdec_dense_store_bytes(int64_t M, int64_t Kd) { return cdiv(M, 128) * cdiv(Kd, kDChunkElems) * (int64_t)kDTileBytes; }
+int64_t lmdec_dense_image_bytes(int64_t Kd, int N) { return cdiv(Kd, kDChunkElems) * kDKb * (int64_t)N * 32; }
+
+int lmdec_dense_pack(const void* src, int dtype, int64_t rows, int64_t cols, int64_t ld, int transpose, float* store,
+                     void* stream) {
+  if (!src || !store || rows <= 0 || cols <= 0 || ld < cols) return fail("lmdec_dense_pack: bad arguments");
+  const int64_t M = transpose ? cols : rows, Kd = transpose ? rows : cols;
+  const int64_t n_kc = cdiv(Kd, kDChunkElems), n_units = cdiv(M, 128) * n_kc * 1024;
+  const unsigned blocks = (unsigned)(cdiv(n_units, 256) < (1 << 20) ? cdiv(n_units, 256) : (1 << 20));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == 0)
+    dense_pack_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, rows, cols, ld, transpose, store, M, Kd, n_kc, n_units);
+  else if (dtype == 1)
+    dense_pack_kernel<double><<<blocks, 256, 0, st>>>((const double*)src, rows, cols, ld, transpose, store, M, Kd, n_kc,
+                                                      n_units);
+  else
+    return fail("lmdec_dense_pack: dtype must be 0 (float32) or 1 (float64)");
+  return check_launch("lmdec_dense_pack");
+}
+
+int lmdec_dense_unpack(const float* store, int64_t M, int64_t Kd, float* dst, int64_t ld, void* stream) {
+  if (!store || !dst || M <= 0 || Kd <= 0 || ld < Kd) return fail("lmdec_dense_unpack: bad arguments");
+  const int64_t n_kc = cdiv(Kd, kDChunkElems), n_units = cdiv(M, 128) * n_kc * 1024;
+  const unsigned blocks = (unsigned)(cdiv(n_units, 256) < (1 << 20) ? cdiv(n_units, 256) : (1 << 20));
+  dense_unpack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(store, M, Kd, n_kc, dst, ld, n_units);
+  return check_launch("lmdec_dense_unpack");
+}
+
+int lmdec_dense_matmul(lmdec_ctx* ctx_in, const float* store, int64_t M, int64_t Kd, int64_t m_limit, int64_t kd_limit,
+                       const void* B, int b_dtype, int64_t ldb, int K, float* image_hi, float* image_lo, double* out,
+                       int64_t ldo, int splits, void* stream) {
+  if (!store || !B || !image_hi || !image_lo || !out) return fail("lmdec_dense_matmul: null argument");
+  if (K < 1 || K > 128 || ldb < K || ldo < K) return fail("lmdec_dense_matmul: 1 <= K <= 128 operand columns per call");
+  if (m_limit <= 0 || m_limit > M || kd_limit <= 0 || kd_limit > Kd) return fail("lmdec_dense_matmul: bad limits");
+  const lmdec_ctx& ctx = ctx_in ? *ctx_in : kDefaultCtx;
+  int n_sm = ctx.n_sm;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (ctx_in) ctx_in->n_sm = n_sm;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = (K + 15) / 16 * 16;
+  DenseMmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.store = (const uint8_t*)store;
+  p.store_kc = cdiv(Kd, kDChunkElems);
+  p.m_limit = m_limit;
+  p.m_tiles = (int)cdiv(m_limit, 128);
+  p.n_chunks = (int)cdiv(kd_limit, kDChunkElems);
+  p.image_hi = (const uint8_t*)image_hi;
+  p.image_lo = (const uint8_t*)image_lo;
+  p.K = K;
+  p.N = N;
+  p.out = out;
+  p.ldo = ldo;
+  // operand images (rows beyond kd_limit are zero: a row prefix of the contraction needs no masking of the store)
+  {
+    const int64_t n_units = (int64_t)p.n_chunks * (kDChunkElems / 4) * N;
+    const unsigned blocks = (unsigned)(cdiv(n_units, 256) < (1 << 20) ? cdiv(n_units, 256) : (1 << 20));
+    if (b_dtype == 0)
+      dense_image_kernel<float><<<blocks, 256, 0, st>>>((const float*)B, ldb, kd_limit, K, N, image_hi, image_lo, n_units);
+    else if (b_dtype == 1)
+      dense_image_kernel<double><<<blocks, 256, 0, st>>>((const double*)B, ldb, kd_limit, K, N, image_hi, image_lo, n_units);
+    else
+      return fail("lmdec_dense_matmul: b_dtype must be 0 (float32) or 1 (float64)");
+  }
+  // contraction ranges: enough work items to fill the SMs several times over when there are few m-tiles (A^T y of a
+  // tall matrix), and never more than 2,048 chunks (65,536 elements) summed in one float32 accumulator
+  int want = splits;
+  if (want <= 0) {
+    want = 1;
+    if (p.m_tiles < 4 * n_sm) want = (int)cdiv(8 * (int64_t)n_sm, p.m_tiles);
+    if (want > p.n_chunks / 16) want = p.n_chunks / 16 > 1 ? p.n_chunks / 16 : 1;
+  }
+  const int min_splits = (int)cdiv(p.n_chunks, 2048);
+  if (want < min_splits) want = min_splits;
+  if (want > p.n_chunks) want = p.n_chunks;
+  const int cps = (int)cdiv(p.n_chunks, want);
+  p.splits = (int)cdiv(p.n_chunks, cps);
+  if (p.splits > 1) {
+    if (ldo == K) cudaMemsetAsync(out, 0, (size_t)m_limit * K * sizeof(double), st);
+    else cudaMemset2DAsync(out, (size_t)ldo * sizeof(double), 0, (size_t)K * sizeof(double), (size_t)m_limit, st);
+  }
+  const size_t stage_bytes = (size_t)2 * kDKb * N * 32;
+  const size_t budget = 223 * 1024;
+  int tile_stages = (int)((budget - kDBStages * stage_bytes) / kDTileBytes);
+  if (tile_stages > kDMaxTileStages) tile_stages = kDMaxTileStages;
+  if (tile_stages < 2) return fail("lmdec_dense_matmul: shared memory budget");
+  p.tile_stages = tile_stages;
+  const size_t smem = (size_t)tile_stages * kDTileBytes + kDBStages * stage_bytes;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(dense_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+    if (e != cudaSuccess) return fail("lmdec_dense_matmul: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int n_work = p.m_tiles * p.splits;
+  const int grid = n_work < n_sm ? n_work : n_sm;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ctx.timing) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+  }
+  dense_mma_kernel<<<grid, kDThreads, smem, st>>>(p);
+  if (ctx.timing) {
+    cudaEventRecord(ev1, st);
+    ctx_in->events.emplace_back(ev0, ev1);
+  }
+  return check_launch("lmdec_dense_matmul", 2);
 }
 
 }  // extern "C"
