@@ -23,8 +23,12 @@
 //   warps 8-15  producers: read their row's 64 bytes of the float32 tile from the smem ring, split hi / lo in registers
 //               (two integer operations + one FADD per element), tcgen05.st both into the TMEM operand ring
 //   warp  16    tile loader: cp.async.bulk of whole 16 KB store tiles (128 rows x 32 elements) into the smem ring
-//   warp  17    MMA issuer (one elected lane): 12 MMAs per chunk, alternating two accumulator sets
-//   warp  18    B loader: cp.async.bulk of the hi / lo operand images (K-major, no-swizzle core-matrix order)
+//   warps 17-18 MMA issuers (one elected lane each) on ALTERNATE chunks, 12 MMAs per chunk into the same accumulator.
+//               A single issuer spends 60 % of its time issuing (the issue blocks on the tensor pipe) and 30 % in its
+//               barrier waits, during which the pipe runs dry (profiles/r02/dense_waits.txt); with two, one waits for
+//               its operands while the other issues.  They hand over in strict turn (one mbarrier hop per chunk), so
+//               the order of the float32 additions -- and with it every bit of the result -- is fixed.
+//   warp  19    B loader: cp.async.bulk of the hi / lo operand images (K-major, no-swizzle core-matrix order)
 // A K-block of kind::tf32 is 8 elements = 32 bytes: byte for byte the operand geometry of kind::i8 (32 int8), so the
 // TMEM addressing and the shared-memory descriptors are the ones geno_mma.cuh uses.
 #pragma once
@@ -33,8 +37,13 @@
 namespace lmdec {
 
 constexpr int kDEpilogueWarps = 8, kDProducerWarps = 8;
-constexpr int kDEpilogueWarp0 = 0, kDProducerWarp0 = 8, kDTileLoaderWarp = 16, kDIssuerWarp = 17, kDBLoaderWarp = 18;
-constexpr int kDThreads = 19 * 32;
+#ifndef LMDEC_DENSE_ISSUERS
+#define LMDEC_DENSE_ISSUERS 2
+#endif
+constexpr int kDIssuers = LMDEC_DENSE_ISSUERS;            // 1 or 2
+constexpr int kDEpilogueWarp0 = 0, kDProducerWarp0 = 8, kDTileLoaderWarp = 16, kDIssuerWarp = 17,
+              kDBLoaderWarp = kDIssuerWarp + kDIssuers;
+constexpr int kDThreads = (kDBLoaderWarp + 1 + 3) / 4 * 4 * 32;   // whole warpgroups (setmaxnreg is per warpgroup)
 #ifndef LMDEC_DENSE_FLUSH_CHUNKS
 #define LMDEC_DENSE_FLUSH_CHUNKS 8
 #endif
@@ -47,7 +56,7 @@ constexpr uint32_t kDAccCols = 128;           // TMEM columns per accumulator se
 constexpr uint32_t kDARingCol0 = 2 * kDAccCols, kDAStageCols = 64;   // hi: 32 columns, lo: 32 columns
 // mbarrier slots
 constexpr int kDBarFullT = 0, kDBarEmptyT = 6, kDBarFullA = 12, kDBarEmptyA = 16, kDBarFullB = 20, kDBarEmptyB = 24,
-              kDBarAccFull = 28, kDBarAccEmpty = 30, kDNumBars = 32;
+              kDBarAccFull = 28, kDBarAccEmpty = 30, kDBarTurn = 32, kDNumBars = 34;
 
 struct DenseMmaParams {
   const uint8_t* store;
@@ -77,6 +86,22 @@ __device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+
+// LMDEC_DENSE_PROFILE: CTA 0 prints the cycles each role spent inside its barrier waits (tools/time_dense.py output)
+#ifdef LMDEC_DENSE_PROFILE
+#define DWAIT(acc, stmt) do { const long long t0_ = clock64(); stmt; acc += clock64() - t0_; } while (0)
+#define DWAIT_DECL(...) long long __VA_ARGS__
+#define DWAIT_PRINT(...) do { if (blockIdx.x == 0 && lane == 0) printf(__VA_ARGS__); } while (0)
+#else
+#define DWAIT(acc, stmt) do { stmt; } while (0)
+#define DWAIT_DECL(...) do { } while (0)
+#define DWAIT_PRINT(...) do { } while (0)
+#endif
+
+// Register re-allocation between warpgroups (4 consecutive warps): the epilogue threads hold a whole row of running sums
+// plus a row of freshly loaded partial sums, the single-thread roles need almost nothing.
+template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
 __device__ __forceinline__ uint4 dense_lds128(uint32_t addr) {
   uint4 v;
@@ -115,8 +140,9 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_mma_kernel(const DenseMmaP
       mbar_init(&bars[kDBarEmptyB + i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars[kDBarAccFull + i], 1);
+      mbar_init(&bars[kDBarAccFull + i], kDIssuers);
       mbar_init(&bars[kDBarAccEmpty + i], kDEpilogueWarps);
+      mbar_init(&bars[kDBarTurn + i], 1);
     }
     mbar_fence_init();
   }
@@ -132,18 +158,20 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_mma_kernel(const DenseMmaP
 
   if (warp >= kDProducerWarp0 && warp < kDProducerWarp0 + kDProducerWarps) {
     // ------------------------------------------------------------------ producers: float32 -> (hi, lo) in TMEM
+    reg_dec<72>();
     const int pw = warp - kDProducerWarp0;
     const int q = pw & 3, half = pw >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16) + kDARingCol0 + 16u * half;
     const uint32_t my_off = (uint32_t)(4 * half) * 2048 + (uint32_t)row * 16;   // pieces 4 half .. 4 half + 3
     uint32_t a_stage = 0, a_phase = 0, t_stage = 0, t_phase = 0;
+    DWAIT_DECL(w_tile = 0, w_astage = 0, w_st = 0, t_begin = clock64());
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int sp = w / p.m_tiles;
       const int c0 = sp * chunks_per_split;
       const int c1 = min(c0 + chunks_per_split, p.n_chunks);
       for (int c = c0; c < c1; ++c) {
-        mbar_wait_a(full_t + 8 * t_stage, t_phase);
+        DWAIT(w_tile, mbar_wait_a(full_t + 8 * t_stage, t_phase));
         const uint32_t src = smem_t_a + t_stage * kDTileBytes + my_off;
         uint4 raw[4];
 #pragma unroll
@@ -162,12 +190,12 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_mma_kernel(const DenseMmaP
             lo[4 * i + e] = __float_as_uint(__uint_as_float(x[e]) - __uint_as_float(h));   // exact in float32
           }
         }
-        mbar_wait_a(empty_a + 8 * a_stage, a_phase ^ 1);
+        DWAIT(w_astage, mbar_wait_a(empty_a + 8 * a_stage, a_phase ^ 1));
         tc_fence_after_sync();
         const uint32_t a_addr = lane_addr + a_stage * kDAStageCols;
         tmem_st16(a_addr, hi);
         tmem_st16(a_addr + 32, lo);
-        tmem_wait_st();
+        DWAIT(w_st, tmem_wait_st());
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {
@@ -184,7 +212,11 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_mma_kernel(const DenseMmaP
         }
       }
     }
-  } else if (warp == kDTileLoaderWarp) {
+    if (pw == 0) DWAIT_PRINT("producer 0: total %lld  wait tile %lld  wait A stage %lld  wait::st %lld\n",
+                             clock64() - t_begin, w_tile, w_astage, w_st);
+  } else if (warp >= kDTileLoaderWarp) {
+   reg_dec<40>();                    // warps 16-19: one warpgroup of single-thread roles
+   if (warp == kDTileLoaderWarp) {
     // ------------------------------------------------------------------ store-tile loader
     if (lane == 0) {
       uint32_t t_stage = 0, t_phase = 0;
@@ -225,12 +257,16 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_mma_kernel(const DenseMmaP
         }
       }
     }
-  } else if (warp == kDIssuerWarp) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp >= kDIssuerWarp && warp < kDIssuerWarp + kDIssuers) {
+    // ------------------------------------------------------------------ MMA issuers
+    const uint32_t me = (uint32_t)(warp - kDIssuerWarp);
+    const uint32_t turn_mine = bar0 + 8 * (kDBarTurn + me), turn_other = bar0 + 8 * (kDBarTurn + (me ^ 1u));
     const uint32_t idesc = make_idesc_tf32(128, (uint32_t)N);
     const uint64_t bdesc_ring = make_smem_desc(smem_b_a, (uint32_t)N * 16, 128);
     const uint32_t kb_step = (uint32_t)(2 * N);          // one K-block of the image, in 16-byte units
     uint32_t a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, sub_no = 0;
+    uint32_t gc = 0;                                     // running chunk count of this CTA: issuer gc % kDIssuers owns it
+    DWAIT_DECL(w_acc = 0, w_b = 0, w_a = 0, w_turn = 0, w_issue = 0, t_begin = clock64());
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int sp = w / p.m_tiles;
       const int c0 = sp * chunks_per_split;
@@ -238,28 +274,53 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_mma_kernel(const DenseMmaP
       for (int g0 = c0; g0 < c1; g0 += kDFlushChunks, ++sub_no) {      // one partial accumulator per kDFlushChunks chunks
         const int g1 = min(g0 + kDFlushChunks, c1);
         const uint32_t set = sub_no & 1, set_phase = (sub_no >> 1) & 1;
-        mbar_wait_a(acc_empty + 8 * set, set_phase ^ 1);
+        DWAIT(w_acc, mbar_wait_a(acc_empty + 8 * set, set_phase ^ 1));
         tc_fence_after_sync();
         const uint32_t d_addr = tbase + set * kDAccCols;
-        for (int c = g0; c < g1; ++c) {
-          mbar_wait_a(full_b + 8 * b_stage, b_phase);
-          mbar_wait_a(full_a + 8 * a_stage, a_phase);
-          tc_fence_after_sync();
-          if (elect_one()) {
-            const uint32_t a_hi = tbase + kDARingCol0 + a_stage * kDAStageCols, a_lo = a_hi + 32;
-            const uint64_t b_hi = bdesc_ring + (uint64_t)((b_stage * stage_bytes) >> 4);
-            const uint64_t b_lo = b_hi + (uint64_t)(img_bytes >> 4);
-#pragma unroll
-            for (int kb = 0; kb < kDKb; ++kb) {
-              // small terms first: they are added while the accumulator is still small
-              umma_ts_tf32(d_addr, a_lo + kb * 8, b_hi + kb * kb_step, idesc, (c == g0 && kb == 0) ? 0u : 1u);
-              umma_ts_tf32(d_addr, a_hi + kb * 8, b_lo + kb * kb_step, idesc, 1u);
-              umma_ts_tf32(d_addr, a_hi + kb * 8, b_hi + kb * kb_step, idesc, 1u);
+        bool issued = false;
+        for (int c = g0; c < g1; ++c, ++gc) {
+          if (kDIssuers == 1 || (gc & 1u) == me) {
+            DWAIT(w_b, mbar_wait_a(full_b + 8 * b_stage, b_phase));
+            DWAIT(w_a, mbar_wait_a(full_a + 8 * a_stage, a_phase));
+            if (kDIssuers == 2 && gc > 0) {
+              // my k-th chunk (k = gc / 2) goes after the other issuer's previous one: its arrival number k (me = 1)
+              // or k - 1 (me = 0) on my turn barrier
+              const uint32_t k = gc >> 1;
+              DWAIT(w_turn, mbar_wait_a(turn_mine, (me ? k : k - 1) & 1u));
             }
-            umma_commit_a(empty_a + 8 * a_stage);
-            umma_commit_a(empty_b + 8 * b_stage);
+            tc_fence_after_sync();
+#ifdef LMDEC_DENSE_PROFILE
+            const long long ti_ = clock64();
+#endif
+            if (elect_one()) {
+              const uint32_t a_hi = tbase + kDARingCol0 + a_stage * kDAStageCols, a_lo = a_hi + 32;
+              const uint64_t b_hi = bdesc_ring + (uint64_t)((b_stage * stage_bytes) >> 4);
+              const uint64_t b_lo = b_hi + (uint64_t)(img_bytes >> 4);
+#pragma unroll
+              for (int kb = 0; kb < kDKb; ++kb) {
+#if defined(LMDEC_DENSE_ABL_MMA1)      // ablation (timing only, wrong results): one of the three MMAs
+                umma_ts_tf32(d_addr, a_hi + kb * 8, b_hi + kb * kb_step, idesc, (c == g0 && kb == 0) ? 0u : 1u);
+#elif defined(LMDEC_DENSE_ABL_NOMMA)   // ablation (timing only): barriers and commits, no tensor-core work
+#else
+                // small terms first: they are added while the accumulator is still small
+                umma_ts_tf32(d_addr, a_lo + kb * 8, b_hi + kb * kb_step, idesc, (c == g0 && kb == 0) ? 0u : 1u);
+                umma_ts_tf32(d_addr, a_hi + kb * 8, b_lo + kb * kb_step, idesc, 1u);
+                umma_ts_tf32(d_addr, a_hi + kb * 8, b_hi + kb * kb_step, idesc, 1u);
+#endif
+              }
+              umma_commit_a(empty_a + 8 * a_stage);
+              umma_commit_a(empty_b + 8 * b_stage);
+              if (kDIssuers == 2) {
+                tc_fence_before_sync();
+                mbar_arrive_a(turn_other);          // the other issuer may queue the next chunk behind this one
+              }
+            }
+            __syncwarp();
+            issued = true;
+#ifdef LMDEC_DENSE_PROFILE
+            w_issue += clock64() - ti_;
+#endif
           }
-          __syncwarp();
           if (++a_stage == (uint32_t)kDAStages) {
             a_stage = 0;
             a_phase ^= 1;
@@ -269,12 +330,20 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_mma_kernel(const DenseMmaP
             b_phase ^= 1;
           }
         }
-        if (elect_one()) umma_commit_a(acc_full + 8 * set);
+        // the partial tile is complete when the MMAs of BOTH issuers are: each commits behind its own last chunk
+        if (elect_one()) {
+          if (issued) umma_commit_a(acc_full + 8 * set);
+          else mbar_arrive_a(acc_full + 8 * set);
+        }
         __syncwarp();
       }
     }
+    DWAIT_PRINT("issuer %u: total %lld  wait acc %lld  wait B %lld  wait A %lld  wait turn %lld  issue+commit %lld\n", me,
+                clock64() - t_begin, w_acc, w_b, w_a, w_turn, w_issue);
+   }
   } else if (warp >= kDEpilogueWarp0 && warp < kDEpilogueWarp0 + kDEpilogueWarps) {
     // ------------------------------------------------------------------ epilogue: float32 accumulator -> float64 out
+    reg_inc<144>();   // (144 - 96) x 256 threads <= what the other warpgroups gave back: (96 - 72) x 256 + (96 - 40) x 128
     const int e = warp - kDEpilogueWarp0;
     const int quarter = e & 3, colhalf = e >> 2;
     const int n8 = N / 16;                          // groups of 8 columns owned by this thread (N / 2 columns)
@@ -293,19 +362,27 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_mma_kernel(const DenseMmaP
         mbar_wait_relaxed_a(acc_full + 8 * set, set_phase);
         tc_fence_after_sync();
         const uint32_t t_addr = tbase + ((uint32_t)(quarter * 32) << 16) + set * kDAccCols + col0;
+        // two round trips of up to 32 columns each; the set goes back to the issuers as soon as the second has landed
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (g < n8) {
-            uint32_t r[8];
-            tmem_ld8(t_addr + g * 8, r);
-            tmem_wait_ld();
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sum[g * 8 + j] += __uint_as_float(r[j]);    // round-to-nearest float32 adds
+          for (int g = 0; g < 4; ++g)
+            if (4 * h + g < n8) tmem_ld8p(t_addr + (4 * h + g) * 8, r + g * 8);
+          tmem_wait_ld();
+          if (h == 1) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(acc_empty + 8 * set);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (4 * h + g < n8) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) sum[(4 * h + g) * 8 + j] += __uint_as_float(r[g * 8 + j]);   // round-to-nearest adds
+            }
           }
         }
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_a(acc_empty + 8 * set);
       }
       const long long row = (long long)mt * 128 + quarter * 32 + lane;
       if (row < p.m_limit) {
