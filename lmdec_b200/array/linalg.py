@@ -13,7 +13,7 @@ import os
 import numpy as np
 import torch
 
-from ..device import (F64, chol_whiten, cholqr2_grid, cholqr2_grid_fits, cholqr2_small, cholqr2_small_fits, gram,
+from ..device import (F64, GRAM_LIBRARY_MIN_K, chol_whiten, cholqr2_grid, cholqr2_grid_fits, cholqr2_small, cholqr2_small_fits, gram,
                       gram_chol, qr_pack)
 
 
@@ -145,7 +145,7 @@ def orthonormalize_begin(x: torch.Tensor, group=None, stats_for=None) -> _Pendin
             if work is not None:
                 stats_for.qr_stats_emitted(q)
             return _PendingQR(q, packed, K)
-    if group is None:
+    if group is None and K <= GRAM_LIBRARY_MIN_K:
         _, ri1, r1, f1 = gram_chol(x)                  # 2 launches per pass, nothing else
         q1 = x @ ri1
         G2, ri2, r2, f2 = gram_chol(q1)

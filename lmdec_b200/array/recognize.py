@@ -90,6 +90,11 @@ def genotype_operator_from_containers(arr, planes: int = 3) -> Optional[object]:
         impute[col] = val
         if not bool((impute[col] == val).all().item()):        # imputed value must be one number per column
             return None
+    # cheap rejection before anything is packed: a float matrix whose first rows already hold something other than
+    # {0, 1, 2, NaN} is not a genotype matrix (a 16 GB dense member would otherwise be scanned and packed for nothing)
+    head = g.a[:min(n, 64)]
+    if not bool(((head == 0) | (head == 1) | (head == 2) | torch.isnan(head)).all().item()):
+        return None
     store = GenotypeStore(n, p, device=dev)
     rows_per_block = 2048
     for r0 in range(0, n, rows_per_block):

@@ -1730,8 +1730,16 @@ int lmdec_gram_chol(const double* X, int64_t ldx, int64_t m, int K, double rank_
     attr_set = true;
   }
   gram_partial_kernel<<<nb, 256, (size_t)kGramRows * K * sizeof(double), st>>>(X, ldx, nullptr, 0, m, K, work);
-  chol_whiten_kernel<<<1, 128, (size_t)(2 * K * K + K) * sizeof(double), st>>>(work, K, rank_tol, r_inv, r, flag, nb, G);
-  return check_launch("lmdec_gram_chol", 2);
+  if ((int64_t)nb * K * K <= (1 << 18)) {
+    // few partials: the factorisation block sums them itself (one launch less)
+    chol_whiten_kernel<<<1, 128, (size_t)(2 * K * K + K) * sizeof(double), st>>>(work, K, rank_tol, r_inv, r, flag, nb, G);
+    return check_launch("lmdec_gram_chol", 2);
+  }
+  // wide iterates (configs[4]: K = 110, a thousand partial matrices = 100 MB): one thread per matrix element sums them
+  // in block order across the whole GPU; a single block doing it took 8 ms per call
+  gram_final_kernel<<<(unsigned)cdiv(K * K + K, 128), 128, 0, st>>>(work, nb, K, G, nullptr);
+  chol_whiten_kernel<<<1, 128, (size_t)(2 * K * K + K) * sizeof(double), st>>>(G, K, rank_tol, r_inv, r, flag, 0, nullptr);
+  return check_launch("lmdec_gram_chol", 3);
 }
 
 int64_t lmdec_cholqr2_small_max_elems(void) { return (int64_t)kCqrCluster * kCqrSliceDoubles; }

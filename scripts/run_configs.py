@@ -84,7 +84,8 @@ def geno_config(name, n, p, k, miss, tol=1e-4, sbpm=False):
 
 
 def dense_config():
-    """configs[4]: dense float 1M x 4k ChainedArray, k=100 (K=110), sym_mat_mult_start; library GEMM path (fp32)."""
+    """configs[4]: dense float 1M x 4k ChainedArray, k=100 (K=110), sym_mat_mult_start; float32 tile stores, 3xTF32 tcgen05
+    product (csrc/dense_mma.cuh)."""
     from lmdec_b200.array import ChainedArray
     n, p, k = 1_000_000, 4_000, 100
     g = torch.Generator(device=dev).manual_seed(3)
@@ -99,7 +100,8 @@ def dense_config():
                      max_iter=100, factor="n")
     U, S, V = pm.svd(arr, verbose=False)
     torch.cuda.synchronize()
-    res = {"config": "c5 dense float 1Mx4k ChainedArray k=100 (K=110), sym_mat_mult_start, fp32 library GEMM",
+    res = {"config": "c5 dense float 1Mx4k ChainedArray k=100 (K=110), sym_mat_mult_start",
+           "product_path": arr.arrays[0].path,
            "svd_s": time.time() - t0, "iterations": pm.num_iter, "S_top3": np.asarray(S)[:3].tolist()}
     res.update(step_rate(arr, 110, n, p, steps=5))
     res["hbm_frac_of_step"] = (2 * 4.0 * n * p) / (res["ms_per_step"] * 1e-3) / (peaks()["hbm_gbs"] * 1e9)
