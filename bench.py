@@ -347,6 +347,68 @@ def run_target(torch, dist, device, world, rank, group, planes):
     return out
 
 
+def run_dense(torch, device, reps=5):
+    """BASELINE configs[4] (not the headline workload; reported beside it at N = 1): the two products of a dense float32
+    1M x 4k operator with K = 110 on the tcgen05 3xTF32 kernel (csrc/dense_mma.cuh) -- HBM-bound by its algorithmic bytes
+    (4 n p per product), so the figure of merit is GB/s against the measured HBM roofline; the library float32 GEMM
+    (cuBLAS through torch) is timed beside it and both are compared with each other."""
+    from lmdec_b200.array.operators import DenseOperator
+    n, p, K = 1_000_000, 4000, 110
+    g = torch.Generator(device=device).manual_seed(3)
+    a = torch.empty((n, p), dtype=torch.float32, device=device)
+    for r0 in range(0, n, 65536):
+        a[r0:r0 + 65536].normal_(generator=g)
+    t = torch.randn((p, K), generator=g, dtype=torch.float64, device=device)
+    y = torch.randn((n, K), generator=g, dtype=torch.float64, device=device)
+
+    def timeit(fn, reps):
+        for _ in range(2):
+            r = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, r
+
+    op = DenseOperator(a, keep_dtype=True)
+    if op.path != "tcgen05":
+        return {"error": "dense operator did not take the tcgen05 path"}
+    tiles = op._native_tiles()
+    tiles.store(False), tiles.store(True)
+    out = {"workload": "configs[4]: dense float32 1,000,000 x 4,000, K = 110 (k = 100 + buffer 10)",
+           "kernel": "dense_mma_kernel (tcgen05 kind::tf32, 3xTF32, float32 accumulation)", "bound": "hbm"}
+    res = {}
+    for name, fn in (("dot", lambda: op.dot_t(t)), ("tdot", lambda: op.tdot_t(y))):
+        tiles.ctx.timing(True)
+        ms, r = timeit(fn, reps)
+        k_ms, k_n = tiles.ctx.timing_read()
+        tiles.ctx.timing(False)
+        res[name] = r
+        out[name + "_ms"] = ms
+        out[name + "_kernel_ms"] = k_ms / max(k_n, 1)
+    pk = peaks()
+    k_avg = 0.5 * (out["dot_kernel_ms"] + out["tdot_kernel_ms"])
+    out["achieved_GBs"] = 4.0 * n * p / (k_avg * 1e-3) / 1e9
+    out["peak_GBs"] = pk["hbm_gbs"]
+    out["frac"] = out["achieved_GBs"] / pk["hbm_gbs"]
+    DenseOperator.native = False
+    try:
+        op2 = DenseOperator(a, keep_dtype=True)
+        ms_d, x_c = timeit(lambda: op2.dot_t(t), 2)
+        ms_t, w_c = timeit(lambda: op2.tdot_t(y), 2)
+        out["cublas_fp32_dot_ms"], out["cublas_fp32_tdot_ms"] = ms_d, ms_t
+        out["max_rel_diff_vs_cublas_fp32"] = max(float((res["dot"] - x_c).abs().max() / x_c.abs().max()),
+                                                 float((res["tdot"] - w_c).abs().max() / w_c.abs().max()))
+    finally:
+        DenseOperator.native = True
+    del a, op, tiles, res
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -501,6 +563,13 @@ def run_ours(args):
         except Exception as e:      # never lose the headline line to the extra
             target = {"error": f"{type(e).__name__}: {e}"}
 
+    dense = None
+    if world == 1 and args.dense:
+        try:
+            dense = run_dense(torch, device)
+        except Exception as e:      # never lose the headline line to the extra
+            dense = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         pk = peaks()
         avg_kernel_ms = mma_total_ms / max(mma_launches, 1)
@@ -545,6 +614,8 @@ def run_ours(args):
         }
         if target is not None:
             line["target"] = target
+        if dense is not None:
+            line["configs4_dense"] = dense
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = {k: v for k, v in cpu_step_throughput(3, 1).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
@@ -565,6 +636,8 @@ def main():
     ap.add_argument("--no-target", dest="target", action="store_false",
                     help="skip the north-star problem (100k x 500k, row-sharded, run to convergence)")
     ap.add_argument("--target-only", action="store_true", help="run only the north-star problem (key `target`)")
+    ap.add_argument("--no-dense", dest="dense", action="store_false",
+                    help="skip the configs[4] dense float products (N = 1 only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps")
     args = ap.parse_args()

@@ -178,6 +178,22 @@ int lmdec_operator_apply(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_
                          int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, void* out, int64_t ldo,
                          void* stream);
 
+/* A^T y fused with its all-reduce over sample-row shards (the "p x k allreduce of A^T.Y" of the north-star partitioning;
+ * reference: the same `A.T.dot(q)` of iter_methods.py:383, whose row chunks dask sums).  As lmdec_operator_apply with
+ * transpose and float32 output, but the epilogue of the tensor-core kernel ADDS every finished 128 x K tile into all
+ * ranks' copies of `out` through `out_multicast`, the NVSwitch multicast address of the same symmetric allocation
+ * (`multimem.red.add.f32`): the reduction overlaps the product tile by tile and no collective follows the kernel.
+ * Contract: `out` (this rank's replica, leading dimension K, K % 4 == 0) is zero on EVERY rank before ANY rank launches,
+ * and is complete on a rank once every rank's launch has finished (one cross-rank barrier; the host side uses the signal
+ * pads of torch's symmetric memory).  Returns 3, having launched no product, when the reduction cannot be fused (the
+ * contraction would have to be split, or shared memory has no room for the staged epilogue): fall back to
+ * lmdec_operator_apply + an all-reduce.  The sum order over ranks is not fixed: float32 round-off differs run to run. */
+int lmdec_operator_apply_reduce(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit,
+                                int64_t kd_limit, int has_missing, int transpose_flags, const void* B, int64_t ldb, int K,
+                                int P, const double* scale, const double* impute, const double* center_w, double* work,
+                                int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, float* out,
+                                float* out_multicast, void* stream);
+
 /* The whole step of the power iteration in ONE call (SURVEY 8b `lmdec_apass`): the Gram operator applied to an
  * orthonormal block,   t = A^T q  (p x K float32, kept: V and the v-subspace / rmse metrics reuse it)   and
  * x = A t * inv_factor  (n_limit x K float64) -- `x = A.dot(A.T.dot(q)) / factor` of PowerMethod._solution_step

@@ -38,6 +38,8 @@ SIGNATURES = {
     "lmdec_apply_work_doubles": (_i64, [_i32]),
     "lmdec_operator_apply": (_i32, [_p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p,
                                     _p, _p, _p, _p, _i64, _p]),
+    "lmdec_operator_apply_reduce": (_i32, [_p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _p,
+                                           _p, _p, _p, _p, _p, _p, _p]),
     "lmdec_apass": (_i32, [_p, _p, _p, _i64, _i64, _i64, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p,
                            _p, _p, _p, _i64, C.c_double, _p]),
     "lmdec_chol_whiten": (_i32, [_p, _i32, C.c_double, _p, _p, _p, _p]),

@@ -101,6 +101,11 @@ struct FusedFinalize {
   double* stats_final;
   double stats_lim;
   unsigned int* stats_ticket;   // device counter, zero between launches
+  // optional (float32 output, staged epilogue): NVSwitch multicast alias of `out` in a symmetric allocation shared by the
+  // ranks of a row-sharded run.  The epilogue then ADDS its tile into every rank's replica (multimem.red) instead of
+  // storing it: the all-reduce of t = A^T q happens tile by tile while the tensor cores work on the next tile, and the
+  // separate NCCL all-reduce behind the kernel disappears (out must be zero on every rank before the launch)
+  float* mc_out;
 };
 
 #ifdef LMDEC_TRACE
@@ -575,6 +580,11 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, uint32_t smem_src, uint
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void multimem_red_add_v4(float* mc_addr, const float4& v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void stats_last_cta_fold(const GenoMmaParams& p, int k, int K, double* scratch);
 
 template <int P, int MODE, bool kStats>
@@ -686,7 +696,13 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
       asm volatile("bar.sync 1, %0;" ::"n"(kStatThreads) : "memory");
       if (live_rows > 0) {
         float* gdst = (float*)p.fz.out + m0 * p.fz.ldo;
-        if (bulk) {
+        if (p.fz.mc_out) {
+          // fused all-reduce: the staged tile is added into every rank's copy of t through the NVSwitch multicast
+          // address (in-switch reduction), 16 bytes per instruction; ldo == K and K % 4 == 0 are checked at launch
+          float* mdst = p.fz.mc_out + m0 * K;
+          const float4* s4 = reinterpret_cast<const float4*>(sy);
+          for (int i = et; i < live_rows * K / 4; i += kStatThreads) multimem_red_add_v4(mdst + 4 * i, s4[i]);
+        } else if (bulk) {
           if (et == 0) bulk_s2g(gdst, smem_u32(sy), bytes);
         } else {
           for (int i = et; i < live_rows * K; i += kStatThreads) gdst[(long long)(i / K) * p.fz.ldo + i % K] = sy[i];
@@ -707,6 +723,7 @@ __device__ __forceinline__ void epilogue_loop32(const GenoMmaParams& p, uint32_t
   }
   LMDEC_WAITOUT(0, ew == 0 && lane == 0);
   if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (p.fz.mc_out) __threadfence_system();    // the reductions sent to the peers are ordered before the kernel's end
   if (kStats) {
     fold_mx[ew * 32 + lane] = mx;
     fold_sm[ew * 32 + lane] = sm;

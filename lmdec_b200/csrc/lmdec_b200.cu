@@ -1373,6 +1373,7 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
     if (fused) *fused = true;
   }
   if (stats_emitted) *stats_emitted = p.fuse == 2;
+  if (fz && fz->mc_out && !p.fuse) return fail("lmdec_operator_apply_reduce: the contraction is split, nothing to fuse into") + 2;
   const size_t stage_bytes = (size_t)8 * N * 32 * p.n_img;
   const size_t budget = 223 * 1024 - 512;  // 227 KB per CTA minus the static barriers / column constants (4 KB), slack
   // shared memory behind the rings: the float32 epilogue's staging area (two output tiles, per-row factors, fold
@@ -1385,6 +1386,8 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
     if (scratch + (size_t)2 * kTileBytes + 2 * stage_bytes <= budget) p.epi_staged = 1;
     else scratch = 0;
   }
+  if (p.fuse && p.fz.mc_out && !p.epi_staged)
+    return fail("lmdec_operator_apply_reduce: no room for the staged float32 epilogue") + 2;
   if (p.fuse == 2 && !p.epi_staged) {
     const int split = kEpilogueWarps / 4;
     int cols = 0;
@@ -1553,11 +1556,13 @@ static int launch_colstats(const void* B, bool b_f32, int64_t ldb, int64_t kd_li
   return check_launch("lmdec_operator_apply (colstats)", 2);
 }
 
-int lmdec_operator_apply(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit,
-                         int64_t kd_limit, int has_missing, int transpose_flags, const void* B, int64_t ldb, int K, int P,
-                         const double* scale, const double* impute, const double* center_w, double* work,
-                         int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, void* out, int64_t ldo,
-                         void* stream) {
+}  // extern "C"
+
+static int operator_apply_impl(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit,
+                               int64_t kd_limit, int has_missing, int transpose_flags, const void* B, int64_t ldb, int K,
+                               int P, const double* scale, const double* impute, const double* center_w, double* work,
+                               int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, void* out, int64_t ldo,
+                               void* stream, float* mc_out) {
   if (K < 1 || K > 128 || P < 1 || P > 4) return fail("lmdec_operator_apply: bad K/P");
   const int transpose = transpose_flags & 1;
   const bool reuse_operand = (transpose_flags & 2) != 0;  // stats + plane images of B are already in work / image1/2
@@ -1611,10 +1616,14 @@ int lmdec_operator_apply(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_
   fz.stats_final = emit_stats ? stats : nullptr;    // (the kernel has read its own colscale / colshift by then)
   fz.stats_lim = lim_next;
   fz.stats_ticket = ticket;
+  fz.mc_out = mc_out;
+  if (mc_out && (!transpose || !out_f32 || emit_stats || ldo != K || (K & 3) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+                 (reinterpret_cast<uintptr_t>(mc_out) & 15)))
+    return fail("lmdec_operator_apply_reduce: needs A^T y, float32 output, ldo == K, K % 4 == 0, 16-byte alignment");
   bool fused = false, emitted = false;
   rc = launch_geno_mma(ctx, store, M, Kd, m_limit, kd_limit, has_missing, (transpose && has_missing) ? 1 : 0, image1,
-                       two ? image2 : nullptr, K, P, N, acc0, (transpose && has_missing) ? acc1 : nullptr, 0, stream,
-                       &fz, &fused, &emitted);
+                       two ? image2 : nullptr, K, P, N, acc0, (transpose && has_missing) ? acc1 : nullptr,
+                       mc_out ? 1 : 0, stream, &fz, &fused, &emitted);
   if (rc) return rc;
   if (!fused) {
     if (!out_f32)
@@ -1633,6 +1642,27 @@ int lmdec_operator_apply(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_
     rc = launch_colstats(out, out_f32, ldo, m_limit, K, scale, has_missing ? impute : nullptr, center_w,
                          center_w != nullptr, lim_next, stats, partial, st);
   return rc;
+}
+
+extern "C" {
+
+int lmdec_operator_apply(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit,
+                         int64_t kd_limit, int has_missing, int transpose_flags, const void* B, int64_t ldb, int K, int P,
+                         const double* scale, const double* impute, const double* center_w, double* work,
+                         int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, void* out, int64_t ldo,
+                         void* stream) {
+  return operator_apply_impl(ctx, store, M, Kd, m_limit, kd_limit, has_missing, transpose_flags, B, ldb, K, P, scale,
+                             impute, center_w, work, image1, image2, acc0, acc1, out, ldo, stream, nullptr);
+}
+
+int lmdec_operator_apply_reduce(lmdec_ctx* ctx, const uint8_t* store, int64_t M, int64_t Kd, int64_t m_limit,
+                                int64_t kd_limit, int has_missing, int transpose_flags, const void* B, int64_t ldb, int K,
+                                int P, const double* scale, const double* impute, const double* center_w, double* work,
+                                int8_t* image1, int8_t* image2, int64_t* acc0, int64_t* acc1, float* out,
+                                float* out_multicast, void* stream) {
+  if (!out_multicast) return fail("lmdec_operator_apply_reduce: null multicast address");
+  return operator_apply_impl(ctx, store, M, Kd, m_limit, kd_limit, has_missing, transpose_flags, B, ldb, K, P, scale,
+                             impute, center_w, work, image1, image2, acc0, acc1, out, K, stream, out_multicast);
 }
 
 __global__ void scale_inplace_kernel(double* __restrict__ x, int64_t m, int K, int64_t ld, double a) {

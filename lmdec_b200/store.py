@@ -538,14 +538,89 @@ class GenotypeOperator:
             w = self._tdot_sharded(y, out_dtype)
         return w[:, 0] if squeeze else w
 
+    # ------------------------------------------------------------------ row-sharded A^T y
+    def _symm_ring(self, K: int):
+        """Three p x K float32 buffers in ONE symmetric allocation shared with the other ranks of the row group (torch
+        symmetric memory: peer-mapped, with an NVSwitch multicast alias), or None when that is not available.  The
+        buffers rotate: a product adds into one while the previous result is still being read and the next is zeroed."""
+        ring = self._buf.get(("symm", K), False)
+        if ring is not False:
+            return ring
+        ring = None
+        st = self.store
+        if os.environ.get("LMDEC_FUSED_REDUCE", "1") != "0" and K % 4 == 0:
+            try:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm_mem
+                n_el = ((st.p * K + 31) // 32) * 32
+                buf = symm_mem.empty((3 * n_el,), dtype=torch.float32, device=st.device)
+                hdl = symm_mem.rendezvous(buf, st.group)
+                ok = torch.tensor([1 if hdl.multicast_ptr else 0], device=st.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=st.group)      # every rank takes the same path
+                if int(ok.item()):
+                    buf.zero_()
+                    hdl.barrier(channel=0)
+                    ring = {"buf": buf, "hdl": hdl, "n_el": n_el, "pos": 0}
+            except Exception as e:      # no symmetric memory / multicast on this box: NCCL all-reduce
+                if os.environ.get("LMDEC_FUSED_REDUCE") == "require":
+                    raise
+                ring = None
+        self._buf[("symm", K)] = ring
+        return ring
+
+    def _tdot_fused_reduce(self, y: torch.Tensor):
+        """A^T y with the all-reduce over the row shards fused into the kernel's epilogue (lmdec_operator_apply_reduce);
+        None when the fused path is not available.  The result is a view of the symmetric ring: it stays valid until the
+        next-but-one product of this operator (the iteration consumes t before that; anything kept longer is copied)."""
+        st, lib = self.store, self.store.lib
+        K = y.shape[1]
+        if self._buf.get(("symm_off", K)):
+            return None
+        ring = self._symm_ring(K)
+        if ring is None:
+            return None
+        buf, hdl, n_el = ring["buf"], ring["hdl"], ring["n_el"]
+        cur = ring["pos"]
+        nxt = (cur + 1) % 3
+        out = buf[cur * n_el: cur * n_el + st.p * K].view(st.p, K)
+        b = self._buffers(K)
+        b.pop("emitted", None)
+        miss = self.has_missing
+        m = self.rows
+        if m > 0:
+            flags = 1 | 8 | (4 if y.dtype == torch.float32 else 0)
+            mc = C.c_void_p(hdl.multicast_ptr + cur * n_el * 4)
+            with _timed("tdot"):
+                rc = lib.lmdec_operator_apply_reduce(
+                    st.ctx.handle, _capi.ptr(st.v_store), st.p, st.n, st.p, m, int(miss), flags, _capi.ptr(y), y.stride(0),
+                    K, self.planes, _capi.ptr(self.inv_std), _capi.ptr(self.impute_mean) if miss else None,
+                    _capi.ptr(self._center_w()), _capi.ptr(b["work"]), _capi.ptr(b["im1"]), _capi.ptr(b["im2"]),
+                    _capi.ptr(b["acc0"]), _capi.ptr(b["acc1"]), _capi.ptr(out), mc, _capi.stream_ptr())
+            if rc == 3:          # cannot be fused for this shape: the same decision on every rank (same shapes), NCCL path
+                self._buf[("symm_off", K)] = True
+                return None
+            _capi.check(rc, "lmdec_operator_apply_reduce")
+        # zero the buffer the NEXT product adds into, then meet the other ranks: behind the barrier every rank's
+        # additions to `out` have landed here and every rank's next buffer is clean
+        buf[nxt * n_el:(nxt + 1) * n_el].zero_()
+        hdl.barrier(channel=0)
+        ring["pos"] = nxt
+        return out
+
     def _tdot_sharded(self, y: torch.Tensor, out_dtype) -> torch.Tensor:
-        """A^T y over row-sharded samples: the p x K partial products (float32 by default, see `wide_dtype`) are
-        all-reduced over NCCL in place.  `reduce_parts` > 1 splits the product into SNP ranges and launches each range's
-        all-reduce asynchronously so that it overlaps the tensor-core work of the next range; measured on 2 x B200 the
-        extra launches cost as much as the overlap wins (profiles/r01/multi_gpu_notes.txt), so the default is 1."""
+        """A^T y over row-sharded samples.  float32 results take the fused path when the box offers NVSwitch multicast:
+        the kernel's epilogue adds each finished tile into every rank's copy of the result (`_tdot_fused_reduce`), one
+        signal-pad barrier follows, no collective.  Otherwise the p x K partial products are all-reduced over NCCL in
+        place.  `reduce_parts` > 1 (NCCL path) splits the product into SNP ranges and launches each range's all-reduce
+        asynchronously; measured on 2 and 8 x B200 the extra launches cost as much as the overlap wins
+        (profiles/r01/multi_gpu_notes.txt, profiles/r02/target_8gpu_parts2.json), so the default is 1."""
         import torch.distributed as dist
         st = self.store
         K = y.shape[1]
+        if out_dtype == torch.float32:
+            w = self._tdot_fused_reduce(y)
+            if w is not None:
+                return w
         w = torch.empty((st.p, K), dtype=out_dtype, device=st.device)
         n_tiles = (st.p + 127) // 128
         parts = max(1, min(int(getattr(st, "reduce_parts", 0) or os.environ.get("LMDEC_REDUCE_PARTS", "1")),
