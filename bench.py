@@ -308,6 +308,7 @@ def run_target(torch, dist, device, world, rank, group, planes):
     else:
         u_full, c_full = u_loc, codes
     out = None
+    fused_reduce = any(isinstance(key, tuple) and key[0] == "symm" and val for key, val in op._buf.items())
     if rank == 0:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import lmdec_oracle as oracle
@@ -327,8 +328,10 @@ def run_target(torch, dist, device, world, rank, group, planes):
         out = {"problem": "top-10 PCA of a 100,000 x 500,000 2-bit genotype matrix (6 synthetic populations, no "
                           "missing codes), centre + binom scale, K = 20, q-vals tol 1e-4, x0 = default_rng(42)",
                "parallelism": "single GPU" if world == 1 else
-                              f"samples row-sharded x{world} (strong scaling): all-reduce of A^T q (p x K float32, 40 MB) "
-                              f"and of the K x K Gram matrices per iteration",
+                              f"samples row-sharded x{world} (strong scaling): reduction of A^T q (p x K float32, 40 MB) "
+                              + ("fused into the product's epilogue (multimem.red through the NVSwitch multicast address)"
+                                 if fused_reduce else "by NCCL all-reduce")
+                              + ", NCCL all-reduce of the K x K Gram matrices",
                "n_gpus": world, "iterations": int(pm.num_iter), "seconds_to_converged": seconds,
                "tflops_to_converged": flops_iter * pm.num_iter / seconds / 1e12,
                "ms_per_iteration": ms_iter, "tflops": flops_iter / (ms_iter * 1e-3) / 1e12,

@@ -44,6 +44,10 @@ def main():
     dist.all_gather_object(u_parts, np.asarray(U))
     ok = True
     if rank == 0:
+        fused = any(isinstance(key, tuple) and key[0] == "symm" and val for key, val in op._buf.items())
+        print(f"[dist_gpu_check world={world}] row shards: A^T q reduction path = "
+              f"{'fused multicast epilogue' if fused else 'NCCL all-reduce'}"
+              f" (LMDEC_FUSED_REDUCE={os.environ.get('LMDEC_FUSED_REDUCE', 'default')})")
         U_all = np.concatenate(u_parts, axis=0)
         op1 = make_snp_array(g)
         pm1 = PowerMethod(**kw)

@@ -86,13 +86,19 @@ def test_two_rank_nccl_parity(cuda):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2): both decompositions of tests/dist_gpu_check.py")
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533",
-                          os.path.join(ROOT, "tests", "dist_gpu_check.py")],
-                         capture_output=True, text=True, timeout=900, env=env)
-    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-4000:]
-    assert "FAIL" not in res.stdout
+    # twice: with the reduction of A^T q fused into the product's epilogue (NVSwitch multicast; falls back by itself
+    # where the box has none) and with the NCCL all-reduce forced
+    paths = []
+    for fused in ("1", "0"):
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", LMDEC_FUSED_REDUCE=fused)
+        res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29533",
+                              os.path.join(ROOT, "tests", "dist_gpu_check.py")],
+                             capture_output=True, text=True, timeout=900, env=env)
+        assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-4000:]
+        assert "FAIL" not in res.stdout
+        paths.append([ln for ln in res.stdout.splitlines() if "reduction path" in ln])
+    assert paths[0] and paths[1] and "NCCL all-reduce" in paths[1][0]
 
 
 # --------------------------------------------------------------------------------------------------------------------
