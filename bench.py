@@ -15,9 +15,12 @@ A "step" is one full iteration of PowerMethod.svd's loop body (accuracy: Cholesk
 A^T q, A t) on data resident in HBM.  `value` = 4 n p K flops per step / time.  `e2e` is the SAME full step through the
 public API with the iterate in HOST memory: x (pinned host) -> H2D -> orthonormalise -> A^T q -> A t -> / n -> D2H.
 
-`--target` (also run by default at N = 8, key "target" of the JSON line): the north-star problem, top-10 PCA of a
-100,000 x 500,000 genotype matrix, samples row-sharded over the N GPUs (strong scaling), run to convergence, with S / V
-checked against the oracle's arithmetic on a column slab.
+Key "target" (every N; `--no-target` skips it): the north-star problem, top-10 PCA of a 100,000 x 500,000 genotype matrix,
+samples row-sharded over the N GPUs (strong scaling; the p x K reduction of A^T q fused into the product kernel's epilogue
+through the NVSwitch multicast address where the box has one), run to convergence, with the product checked against the
+oracle's float64 arithmetic on a column slab.  Key "configs4_dense" (N = 1; `--no-dense` skips it): the two products of
+BASELINE configs[4] (dense float32 1M x 4k, K = 110) on the 3xTF32 tcgen05 kernel, as GB/s against the HBM roofline, with
+the library float32 GEMM timed beside it.
 """
 from __future__ import annotations
 

@@ -98,11 +98,6 @@ __device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, u
 #define DWAIT_PRINT(...) do { } while (0)
 #endif
 
-// Register re-allocation between warpgroups (4 consecutive warps): the epilogue threads hold a whole row of running sums
-// plus a row of freshly loaded partial sums, the single-thread roles need almost nothing.
-template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-
 __device__ __forceinline__ uint4 dense_lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));

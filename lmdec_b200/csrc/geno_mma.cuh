@@ -72,7 +72,17 @@ constexpr int kEpilogueWarp0 = kProducerWarps + 1 + kIssuerWarps;  // consecutiv
 constexpr int kBLoaderWarp = kEpilogueWarp0 + kEpilogueWarps;
 #endif
 static_assert(kProducerWarp0 % 4 == 0 && kEpilogueWarps % 4 == 0, "TMEM lane quarters");  // (epilogue: any 4 consecutive warps)
+// LMDEC_GENO_REGS = 1: setmaxnreg moves registers from the single-thread warps (loaders, issuers) to the epilogue warps,
+// whose finalize variants otherwise spill; needs whole warpgroups (the block is padded to a multiple of 4 warps)
+#ifndef LMDEC_GENO_REGS
+#define LMDEC_GENO_REGS 0
+#endif
+#if LMDEC_GENO_REGS
+static_assert(LMDEC_ROLE_ORDER == 1 && kEpilogueWarps == 8 && kProducerWarps == 8 && kIssuerWarps == 4, "warpgroup layout");
+constexpr int kThreads = ((kProducerWarps + kEpilogueWarps + kIssuerWarps + 2 + 3) / 4) * 4 * 32;
+#else
 constexpr int kThreads = (kProducerWarps + kEpilogueWarps + kIssuerWarps + 2) * 32;
+#endif
 constexpr int kKbPerChunk = 8;             // 8 K-blocks of 32 = one 256-wide contraction chunk = one store tile
 // TMEM: accumulators from column 0, the decoded-A ring behind them up to column 512 (p.a_ring_col0, p.a_stages)
 constexpr int kMaxBStages = 4;
@@ -1210,7 +1220,13 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
     }
     LMDEC_WAITOUT(5, tracer);
     LMDEC_WAITOUT(6, tracer);
+#if LMDEC_GENO_REGS
+  } else if (warp >= kTileLoaderWarp) {
+   reg_dec<40>();          // warps 16-23: loaders, issuers, two idle warps
+   if (warp == kTileLoaderWarp) {
+#else
   } else if (warp == kTileLoaderWarp) {
+#endif
     // ------------------------------------------------------------------ packed-tile loader (TMA bulk copies)
 #ifdef LMDEC_ABL_NOTILESYNC
     if (false) {
@@ -1308,7 +1324,13 @@ __global__ void __launch_bounds__(kThreads, 1) geno_mma_kernel(const GenoMmaPara
       else { if (interleave) LMDEC_ISSUE(kPairNone, false, true); else LMDEC_ISSUE(kPairNone, false, false); }
 #undef LMDEC_ISSUE
     }
+#if LMDEC_GENO_REGS
+   }
   } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + kEpilogueWarps) {
+    reg_inc<120>();         // (120 - 80) x 256 threads = what warps 16-23 gave back: (80 - 40) x 256
+#else
+  } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + kEpilogueWarps) {
+#endif
     // ------------------------------------------------------------------ epilogue
     double* stats_acc = reinterpret_cast<double*>(smem + p.stats_off);
     switch (p.P) {

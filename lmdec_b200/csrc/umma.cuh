@@ -282,6 +282,11 @@ __device__ __forceinline__ void umma_ss_f16(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+// Register re-allocation between warpgroups (4 consecutive warps): the epilogue threads hold a whole row of running sums
+// plus a row of freshly loaded partial sums, the single-thread roles need almost nothing.
+template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
