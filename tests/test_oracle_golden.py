@@ -287,3 +287,30 @@ def test_init_methods():
     x = oracle.sub_svd_init(oracle.as_operator(a), k=5, warm_start_row_factor=10)
     assert x.shape == (200, 5)
     np.testing.assert_array_almost_equal(x.T @ x, np.eye(5))
+
+
+def _separated_matrix():
+    """deterministic 600 x 400 matrix with a separated spectrum 100 * 0.7^i over a flat noise floor (generator committed
+    here)"""
+    rng = np.random.RandomState(7)
+    u, _ = np.linalg.qr(rng.randn(600, 12))
+    v, _ = np.linalg.qr(rng.randn(400, 12))
+    return (u * (100.0 * 0.7 ** np.arange(12))) @ v.T + 1e-3 * rng.randn(600, 400)
+
+
+SEPARATED_S = np.array([100.0, 70.0, 49.0, 34.3, 24.01, 16.807])      # the planted values (the noise moves them by < 1e-4)
+
+
+def test_golden_separated_spectrum_every_singular_value():
+    """the ex1 fixture pins only S[0] tightly (its S[1:] is one cluster).  With a separated spectrum the
+    oracle's PowerMethod must give EVERY singular value and vector of LAPACK's SVD to 1e-8, for all three metrics."""
+    a = _separated_matrix()
+    U, S, Vt = np.linalg.svd(a, full_matrices=False)
+    np.testing.assert_allclose(S[:6], SEPARATED_S, rtol=1e-4)          # fixture sanity: planted values + 1e-3 noise
+    for scoring in ("q-vals", "rmse", "v-subspace"):
+        pm = oracle.PowerMethod(k=6, buffer=6, tol=1e-13, scoring_method=scoring, max_iter=80, factor=None, lmbd=0,
+                                sub_svd_start=False)
+        U_pm, S_pm, V_pm = pm.svd(a, x0=np.random.RandomState(1).randn(600, 12))
+        np.testing.assert_allclose(S_pm, S[:6], rtol=1e-8)
+        assert oracle.subspace_dist(U_pm, U[:, :6], S[:6]) < 1e-10
+        assert oracle.subspace_dist(V_pm.T, Vt[:6].T, S[:6]) < 1e-10
