@@ -86,12 +86,16 @@ constexpr int kThreads = (kProducerWarps + kEpilogueWarps + kIssuerWarps + 2) * 
 constexpr int kKbPerChunk = 8;             // 8 K-blocks of 32 = one 256-wide contraction chunk = one store tile
 // TMEM: accumulators from column 0, the decoded-A ring behind them up to column 512 (p.a_ring_col0, p.a_stages)
 constexpr int kMaxBStages = 4;
-constexpr int kMaxTileStages = 8;
+#ifndef LMDEC_TILE_STAGES
+#define LMDEC_TILE_STAGES 8
+#endif
+constexpr int kMaxTileStages = LMDEC_TILE_STAGES;   // packed tiles in flight per SM (8 KB each)
 constexpr uint32_t kTileBytes = 8192;
 // mbarrier slots (8 bytes each) in one shared array, addressed by 32-bit shared-window addresses
 constexpr int kMaxAStages = 8;
-constexpr int kBarFullT = 0, kBarEmptyT = 8, kBarFullA = 16, kBarEmptyA = 24, kBarFullB = 32, kBarEmptyB = 36,
-              kBarAccFull = 40, kBarAccEmpty = 42, kBarFirstDone = 44, kNumBars = 48;
+constexpr int kBarFullT = 0, kBarEmptyT = kMaxTileStages, kBarFullA = 2 * kMaxTileStages, kBarEmptyA = kBarFullA + 8,
+              kBarFullB = kBarEmptyA + 8, kBarEmptyB = kBarFullB + 4, kBarAccFull = kBarEmptyB + 4,
+              kBarAccEmpty = kBarAccFull + 2, kBarFirstDone = kBarAccEmpty + 2, kNumBars = kBarFirstDone + 4;
 
 // out[m,k] = (acc0 + rowa[m]*acc1) * colscale[k] * rowscale[m] + rowshift[m] * colshift[k]   (NULL = absent / 1)
 struct FusedFinalize {

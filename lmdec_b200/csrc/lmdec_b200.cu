@@ -1418,6 +1418,11 @@ static int launch_geno_mma(lmdec_ctx* ctx_in, const uint8_t* store, int64_t M, i
     if (tile_stages > kMaxTileStages) tile_stages = kMaxTileStages;
     b_stages = p.n_chunks;      // (only sizes the region; the resident image has no ring)
   } else {
+    // the operand ring keeps its full depth first; tiles beyond 8 in flight only from what is left
+    for (; tile_stages > 8; tile_stages -= 2) {
+      b_stages = (int)((budget - scratch - (size_t)tile_stages * kTileBytes) / stage_bytes);
+      if (b_stages >= kMaxBStages) break;
+    }
     for (; tile_stages >= 2; tile_stages /= 2) {
       b_stages = (int)((budget - scratch - (size_t)tile_stages * kTileBytes) / stage_bytes);
       if (b_stages >= 2) break;

@@ -1,5 +1,5 @@
 """Debug timeline of geno_mma_kernel (library built with -DLMDEC_TRACE): per chunk, cycles between the pipeline events
-of CTA 0 (producer warp 0 and issuer 0).  Usage: LMDEC_LIB=ab/lib_trace.so python tools/trace_mma.py [dot|tdot] [miss]"""
+of CTA 0 (producer warp 0 and issuer 0).  Usage: LMDEC_LIB=ab/lib_trace.so python tools/trace_mma.py [dot|tdot] [miss] [n p K]"""
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,7 +11,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "dot"
 miss = float(sys.argv[2]) if len(sys.argv) > 2 else 0.05
 dev = torch.device("cuda", 0)
 lib = _capi.load()
-n, p, K = 2504, 400_000, 20
+n, p, K = (int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])) if len(sys.argv) > 5 else (2504, 400_000, 20)
 store = make_shard(torch, dev, n, p, miss, seed=1)
 mean, std = store.moments("binom")
 op = GenotypeOperator(store, mean, 1.0 / std)
