@@ -141,6 +141,11 @@ int lmdec_gram(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64
                double* work, void* stream);
 
 /* q_value_converge (lmdec/array/metrics.py:219-235): out[0] = ||si-sj||_2 / ((||si||+||sj||)/2) (scale != 0). */
+/* Gram matrix of a row shard ADDED into every rank's copy of a symmetric K x K buffer through its NVSwitch multicast
+ * address (`multimem.red.add.f64`): the "k x k Gram allreduce" of the north-star's CholeskyQR2 without a collective call
+ * (reference: the stacked-R step of dask tsqr, lmdec/decomp/iter_methods.py:382).  The buffer is zero on every rank
+ * before any rank launches and complete after one cross-rank barrier; m = 0 (a rank without rows) launches nothing. */
+int lmdec_gram_reduce(const double* X, int64_t ldx, int64_t m, int K, double* G_multicast, double* work, void* stream);
 int lmdec_qvals(const double* si, const double* sj, int k, int scale, double* out, void* stream);
 /* rmse_k's Frobenius part (metrics.py:161): out[0] = sum_{m,k} (A[m,k] - B[m,k]*s[k])^2  (deterministic). */
 int lmdec_sqdiff(const double* A, int64_t lda, const double* B, int64_t ldb_, const double* s, int64_t m, int K,

@@ -34,6 +34,7 @@ SIGNATURES = {
     "lmdec_finalize": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "lmdec_gram_work_doubles": (_i64, [_i64, _i32]),
     "lmdec_gram": (_i32, [_p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p]),
+    "lmdec_gram_reduce": (_i32, [_p, _i64, _i64, _i32, _p, _p, _p]),
     "lmdec_qvals": (_i32, [_p, _p, _i32, _i32, _p, _p]),
     "lmdec_apply_work_doubles": (_i64, [_i32]),
     "lmdec_operator_apply": (_i32, [_p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p,

@@ -24,6 +24,57 @@ def _allreduce(t: torch.Tensor, group):
     return t
 
 
+_GRAM_RINGS = {}
+
+
+def _gram_allreduce(x: torch.Tensor, group):
+    """sum over the row shards of x^T x.  With NVSwitch multicast the per-rank Gram kernel adds its result straight into
+    every rank's copy of a symmetric K x K buffer (`lmdec_gram_reduce`) and one signal-pad barrier follows -- no NCCL
+    call on the latency-critical K x K reductions of the sharded CholeskyQR2; otherwise Gram kernel + all-reduce."""
+    K = x.shape[1]
+    if group is None or not x.is_cuda or K > GRAM_LIBRARY_MIN_K or x.dtype != F64 \
+            or os.environ.get("LMDEC_FUSED_REDUCE", "1") == "0":
+        return _allreduce(gram(x), group)
+    key = (id(group), K, x.device.index)
+    ring = _GRAM_RINGS.get(key, False)
+    if ring is False:
+        ring = None
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            n_el = ((K * K + 31) // 32) * 32
+            buf = symm_mem.empty((4 * n_el,), dtype=F64, device=x.device)
+            hdl = symm_mem.rendezvous(buf, group)
+            ok = torch.tensor([1 if hdl.multicast_ptr else 0], device=x.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()):
+                buf.zero_()
+                hdl.barrier(channel=0)
+                ring = {"buf": buf, "hdl": hdl, "n_el": n_el, "pos": 0}
+        except Exception:
+            if os.environ.get("LMDEC_FUSED_REDUCE") == "require":
+                raise
+            ring = None
+        _GRAM_RINGS[key] = ring
+    if ring is None:
+        return _allreduce(gram(x), group)
+    from .. import _capi
+    from ..device import _rows, _work
+    lib = _capi.load()
+    buf, hdl, n_el, cur = ring["buf"], ring["hdl"], ring["n_el"], ring["pos"]
+    nxt = (cur + 1) % 4
+    xr = _rows(x)
+    m = xr.shape[0]
+    work = _work(x.device, lib.lmdec_gram_work_doubles(max(m, 1), K))
+    _capi.check(lib.lmdec_gram_reduce(_capi.ptr(xr), xr.stride(0), m, K,
+                                      _capi.C.c_void_p(hdl.multicast_ptr + cur * n_el * 8), _capi.ptr(work),
+                                      _capi.stream_ptr()), "lmdec_gram_reduce")
+    buf[nxt * n_el:(nxt + 1) * n_el].zero_()
+    hdl.barrier(channel=0)
+    ring["pos"] = nxt
+    return buf[cur * n_el: cur * n_el + K * K].view(K, K)
+
+
 def _whiten_factor(G: np.ndarray, rank_tol: float = 1e-12):
     """Return (r_inv, r, deficient) with r_inv^T G r_inv = I on the numerical range of G.
 
@@ -150,10 +201,10 @@ def orthonormalize_begin(x: torch.Tensor, group=None, stats_for=None) -> _Pendin
         q1 = x @ ri1
         G2, ri2, r2, f2 = gram_chol(q1)
     else:
-        G1 = _allreduce(gram(x), group)
+        G1 = _gram_allreduce(x, group)
         ri1, r1, f1 = chol_whiten(G1)
         q1 = x @ ri1
-        G2 = _allreduce(gram(q1), group)
+        G2 = _gram_allreduce(q1, group)
         ri2, r2, f2 = chol_whiten(G2)
     q = q1 @ ri2
     packed = qr_pack(r1, r2, G2, f1, f2)

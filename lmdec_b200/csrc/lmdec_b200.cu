@@ -508,6 +508,17 @@ __global__ void gram_final_kernel(const double* __restrict__ work, int n_blocks,
     colsum[o - K * K] = a;
 }
 
+// the same sum, ADDED into every rank's copy of G through the NVSwitch multicast address of a symmetric K x K buffer
+// (row-sharded CholeskyQR2: the K x K all-reduce of the north-star partitioning without a collective call)
+__global__ void gram_final_reduce_kernel(const double* __restrict__ work, int n_blocks, int K, double* __restrict__ G_mc) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= K * K) return;
+  double a = 0.0;
+  for (int b = 0; b < n_blocks; ++b) a += work[(size_t)b * (K * K + K) + o];
+  asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(G_mc + o), "d"(a) : "memory");
+  __threadfence_system();
+}
+
 // K x K Cholesky whitening in one block (float64, shared memory): G = R^T R with G scaled to unit diagonal first.
 //   r_inv [K,K] and r [K,K] row-major (upper triangular), flag = 1 when G is non-finite, has a non-positive diagonal or
 //   a pivot below rank_tol (the caller then takes the rank-revealing host path).  Replaces the K x K step of dask tsqr
@@ -1518,6 +1529,22 @@ int lmdec_gram(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64
   gram_partial_kernel<<<nb, 256, smem, st>>>(X, ldx, Y, ldy, m, K, work);
   gram_final_kernel<<<(unsigned)cdiv(K * K + K, 128), 128, 0, st>>>(work, nb, K, G, colsum);
   return check_launch("lmdec_gram", 2);
+}
+
+int lmdec_gram_reduce(const double* X, int64_t ldx, int64_t m, int K, double* G_multicast, double* work, void* stream) {
+  if (K < 1 || K > 128) return fail("lmdec_gram_reduce: K out of range (1..128)");
+  if (!G_multicast) return fail("lmdec_gram_reduce: null multicast address");
+  if (m <= 0) return 0;                  // a rank without rows in this prefix adds nothing
+  const int nb = gram_blocks(m);
+  cudaStream_t st = (cudaStream_t)stream;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_set = true;
+  }
+  gram_partial_kernel<<<nb, 256, (size_t)kGramRows * K * sizeof(double), st>>>(X, ldx, nullptr, 0, m, K, work);
+  gram_final_reduce_kernel<<<(unsigned)cdiv(K * K, 128), 128, 0, st>>>(work, nb, K, G_multicast);
+  return check_launch("lmdec_gram_reduce", 2);
 }
 
 int lmdec_qvals(const double* si, const double* sj, int k, int scale, double* out, void* stream) {
