@@ -334,7 +334,8 @@ def run_target(torch, dist, device, world, rank, group, planes):
                               f"samples row-sharded x{world} (strong scaling): reduction of A^T q (p x K float32, 40 MB) "
                               + ("fused into the product's epilogue (multimem.red through the NVSwitch multicast address)"
                                  if fused_reduce else "by NCCL all-reduce")
-                              + ", NCCL all-reduce of the K x K Gram matrices",
+                              + (", K x K Gram matrices reduced the same way" if fused_reduce
+                                 else ", NCCL all-reduce of the K x K Gram matrices"),
                "n_gpus": world, "iterations": int(pm.num_iter), "seconds_to_converged": seconds,
                "tflops_to_converged": flops_iter * pm.num_iter / seconds / 1e12,
                "ms_per_iteration": ms_iter, "tflops": flops_iter / (ms_iter * 1e-3) / 1e12,
