@@ -39,22 +39,24 @@ def _gram_allreduce(x: torch.Tensor, group):
     ring = _GRAM_RINGS.get(key, False)
     if ring is False:
         ring = None
+        import torch.distributed as dist
+        buf = hdl = None
+        n_el = ((K * K + 31) // 32) * 32
         try:
-            import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
-            n_el = ((K * K + 31) // 32) * 32
             buf = symm_mem.empty((4 * n_el,), dtype=F64, device=x.device)
             hdl = symm_mem.rendezvous(buf, group)
-            ok = torch.tensor([1 if hdl.multicast_ptr else 0], device=x.device)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-            if int(ok.item()):
-                buf.zero_()
-                hdl.barrier(channel=0)
-                ring = {"buf": buf, "hdl": hdl, "n_el": n_el, "pos": 0}
+            mine = 1 if hdl.multicast_ptr else 0
         except Exception:
             if os.environ.get("LMDEC_FUSED_REDUCE") == "require":
                 raise
-            ring = None
+            mine = 0
+        ok = torch.tensor([mine], device=x.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)          # every rank takes the same path
+        if int(ok.item()):
+            buf.zero_()
+            hdl.barrier(channel=0)
+            ring = {"buf": buf, "hdl": hdl, "n_el": n_el, "pos": 0}
         _GRAM_RINGS[key] = ring
     if ring is None:
         return _allreduce(gram(x), group)

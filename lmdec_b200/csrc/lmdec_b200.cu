@@ -525,7 +525,7 @@ __global__ void gram_final_reduce_kernel(const double* __restrict__ work, int n_
 //   (lmdec/decomp/iter_methods.py:382) without a device->host round trip.
 // `n_partials` > 0: G is not a matrix but the per-block partial Gram matrices of gram_partial_kernel (stride
 // K*K + K); they are summed here in block order (deterministic) and the sum is also written to g_out.
-__global__ void __launch_bounds__(128) chol_whiten_kernel(const double* __restrict__ G, int K, double rank_tol,
+__global__ void __launch_bounds__(256) chol_whiten_kernel(const double* __restrict__ G, int K, double rank_tol,
                                                           double* __restrict__ r_inv, double* __restrict__ r,
                                                           int* __restrict__ flag, int n_partials,
                                                           double* __restrict__ g_out) {
@@ -569,31 +569,41 @@ __global__ void __launch_bounds__(128) chol_whiten_kernel(const double* __restri
     Li[i] = 0.0;
   }
   __syncthreads();
-  // right-looking Cholesky: thread t owns row t
+  // right-looking Cholesky, the whole block on every elimination step: the pivot column is scaled, then the trailing
+  // (K - j - 1)^2 / 2 elements are updated in parallel (K = 110: 0.33 ms with one thread per row, ~20 us this way)
+  const int nt = blockDim.x;
   for (int j = 0; j < K; ++j) {
-    if (t == j) {
-      const double piv = L[j * K + j];
+    const double piv = L[j * K + j];
+    const double s = sqrt(piv > rank_tol ? piv : rank_tol);
+    __syncthreads();                         // everybody has read the pivot before it is overwritten
+    if (t == 0) {
       if (!(piv >= rank_tol)) bad = 1;
-      L[j * K + j] = sqrt(piv > rank_tol ? piv : rank_tol);
+      L[j * K + j] = s;
     }
+    for (int r = j + 1 + t; r < K; r += nt) L[r * K + j] /= s;
     __syncthreads();
-    if (t > j && t < K) L[t * K + j] /= L[j * K + j];
-    __syncthreads();
-    if (t > j && t < K) {
-      const double ltj = L[t * K + j];
-      for (int c = j + 1; c <= t; ++c) L[t * K + c] -= ltj * L[c * K + j];
+    const int m = K - j - 1;
+    for (int idx = t; idx < m * m; idx += nt) {
+      const int r = j + 1 + idx / m, c = j + 1 + idx % m;
+      if (c <= r) L[r * K + c] -= L[r * K + j] * L[c * K + j];
     }
     __syncthreads();
   }
-  // inverse of the lower factor by forward substitution: thread t owns column t of Li
-  if (t < K) {
-    for (int i = t; i < K; ++i) {
-      double acc = (i == t) ? 1.0 : 0.0;
-      for (int c = t; c < i; ++c) acc -= L[i * K + c] * Li[c * K + t];
-      Li[i * K + t] = acc / L[i * K + i];
-    }
-  }
+  // inverse of the lower factor, right-looking: row j of Li is final after its scaling, then it is eliminated from the
+  // rows below (rank-1 update of (K - j - 1) x (j + 1) elements in parallel).  Li starts as the identity.
+  for (int i = t; i < K; i += nt) Li[i * K + i] = 1.0;
   __syncthreads();
+  for (int j = 0; j < K; ++j) {
+    const double dj = 1.0 / L[j * K + j];
+    for (int c = t; c <= j; c += nt) Li[j * K + c] *= dj;
+    __syncthreads();
+    const int w = j + 1, m = K - j - 1;
+    for (int idx = t; idx < m * w; idx += nt) {
+      const int r = j + 1 + idx / w, c = idx % w;
+      Li[r * K + c] -= L[r * K + j] * Li[j * K + c];
+    }
+    __syncthreads();
+  }
   // G = D L L^T D  =>  r = L^T D (upper),  r_inv = D^-1 L^-T (upper)
   for (int i = t; i < K * K; i += blockDim.x) {
     const int a = i / K, b = i - a * K;  // element (a, b)
@@ -1740,7 +1750,7 @@ int lmdec_chol_whiten(const double* G, int K, double rank_tol, double* r_inv, do
     cudaFuncSetAttribute(chol_whiten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     attr_set = true;
   }
-  chol_whiten_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(G, K, rank_tol, r_inv, r, flag, 0, nullptr);
+  chol_whiten_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(G, K, rank_tol, r_inv, r, flag, 0, nullptr);
   return check_launch("lmdec_chol_whiten");
 }
 
@@ -1794,13 +1804,13 @@ int lmdec_gram_chol(const double* X, int64_t ldx, int64_t m, int K, double rank_
   gram_partial_kernel<<<nb, 256, (size_t)kGramRows * K * sizeof(double), st>>>(X, ldx, nullptr, 0, m, K, work);
   if ((int64_t)nb * K * K <= (1 << 18)) {
     // few partials: the factorisation block sums them itself (one launch less)
-    chol_whiten_kernel<<<1, 128, (size_t)(2 * K * K + K) * sizeof(double), st>>>(work, K, rank_tol, r_inv, r, flag, nb, G);
+    chol_whiten_kernel<<<1, 256, (size_t)(2 * K * K + K) * sizeof(double), st>>>(work, K, rank_tol, r_inv, r, flag, nb, G);
     return check_launch("lmdec_gram_chol", 2);
   }
   // wide iterates (configs[4]: K = 110, a thousand partial matrices = 100 MB): one thread per matrix element sums them
   // in block order across the whole GPU; a single block doing it took 8 ms per call
   gram_final_kernel<<<(unsigned)cdiv(K * K + K, 128), 128, 0, st>>>(work, nb, K, G, nullptr);
-  chol_whiten_kernel<<<1, 128, (size_t)(2 * K * K + K) * sizeof(double), st>>>(G, K, rank_tol, r_inv, r, flag, 0, nullptr);
+  chol_whiten_kernel<<<1, 256, (size_t)(2 * K * K + K) * sizeof(double), st>>>(G, K, rank_tol, r_inv, r, flag, 0, nullptr);
   return check_launch("lmdec_gram_chol", 3);
 }
 

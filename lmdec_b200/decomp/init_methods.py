@@ -22,12 +22,26 @@ def _local_slice(array, n_global):
     return slice(0, n_global)
 
 
+DEVICE_RNG_MIN_ELEMS = 1 << 24
+
+
 def rnormal_start(array, k: int, seed: int = 42, log: int = 0):
     """N(0,1) start [n, k].  The reference draws from dask's chunked RandomState(seed) (init_methods.py:180-184), whose
     stream depends on the dask chunking; here it is NumPy's RandomState(seed) drawn on the host (global matrix, so every
-    sharding sees the same start) and moved to the device."""
+    sharding sees the same start) and moved to the device.  Unsharded starts of DEVICE_RNG_MIN_ELEMS values or more
+    (configs[4]: 1M x 110, 1.6 s of host RNG -- three quarters of the whole time-to-converged) are drawn by the device
+    generator with the same seed instead: a different, equally seeded stream (the RNG stream is unpinned either way)."""
     array = as_operator(array)
     n = array.shape[0]
+    store = getattr(array, "store", None)
+    sharded = store is not None and (store.group is not None or store.snp_group is not None)
+    if n * k >= DEVICE_RNG_MIN_ELEMS and not sharded:
+        import torch
+        from ..device import F64, require_cuda
+        dev = require_cuda()
+        gen = torch.Generator(device=dev).manual_seed(int(seed))
+        out = DeviceArray(torch.randn((n, k), generator=gen, dtype=F64, device=dev))
+        return (out, {}) if log else out
     omega = np.random.RandomState(seed).standard_normal(size=(n, k))
     out = DeviceArray(as_tensor(omega[_local_slice(array, n)]))
     return (out, {}) if log else out

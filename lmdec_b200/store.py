@@ -549,22 +549,24 @@ class GenotypeOperator:
         ring = None
         st = self.store
         if os.environ.get("LMDEC_FUSED_REDUCE", "1") != "0" and K % 4 == 0:
+            import torch.distributed as dist
+            buf = hdl = None
+            n_el = ((st.p * K + 31) // 32) * 32
             try:
-                import torch.distributed as dist
                 import torch.distributed._symmetric_memory as symm_mem
-                n_el = ((st.p * K + 31) // 32) * 32
                 buf = symm_mem.empty((3 * n_el,), dtype=torch.float32, device=st.device)
                 hdl = symm_mem.rendezvous(buf, st.group)
-                ok = torch.tensor([1 if hdl.multicast_ptr else 0], device=st.device)
-                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=st.group)      # every rank takes the same path
-                if int(ok.item()):
-                    buf.zero_()
-                    hdl.barrier(channel=0)
-                    ring = {"buf": buf, "hdl": hdl, "n_el": n_el, "pos": 0}
-            except Exception as e:      # no symmetric memory / multicast on this box: NCCL all-reduce
+                mine = 1 if hdl.multicast_ptr else 0
+            except Exception:           # no symmetric memory / multicast on this box: NCCL all-reduce
                 if os.environ.get("LMDEC_FUSED_REDUCE") == "require":
                     raise
-                ring = None
+                mine = 0
+            ok = torch.tensor([mine], device=st.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=st.group)      # every rank takes the same path
+            if int(ok.item()):
+                buf.zero_()
+                hdl.barrier(channel=0)
+                ring = {"buf": buf, "hdl": hdl, "n_el": n_el, "pos": 0}
         self._buf[("symm", K)] = ring
         return ring
 
