@@ -70,7 +70,7 @@ def lib_path() -> str:
     return _build.LIB
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 def load():

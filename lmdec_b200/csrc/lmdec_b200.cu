@@ -1177,7 +1177,7 @@ using namespace lmdec;
 extern "C" {
 
 const char* lmdec_last_error(void) { return g_err; }
-int lmdec_abi_version(void) { return 2; }
+int lmdec_abi_version(void) { return 3; }   // 3: + lmdec_dense_*, lmdec_operator_apply_reduce, lmdec_gram_reduce
 #ifndef LMDEC_SRC_HASH
 #define LMDEC_SRC_HASH "unknown"
 #endif
