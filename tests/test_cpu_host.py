@@ -25,6 +25,15 @@ def test_capi_exports_every_declared_symbol():
     assert lib.lmdec_store_bytes(1, 1) == 8192
     assert lib.lmdec_store_bytes(2504, 1_000_000) == 20 * 3907 * 8192
     assert lib.lmdec_image_bytes(1_000_000, 64) == 3907 * 8 * 64 * 32
+    assert lib.lmdec_dense_store_bytes(1, 1) == 16384                       # one tile of 128 rows x 32 float32
+    assert lib.lmdec_dense_store_bytes(1_000_000, 4000) == 7813 * 125 * 16384
+    assert lib.lmdec_dense_image_bytes(4000, 112) == 125 * 4 * 112 * 32
+    # argument validation of the round-2 entry points happens before anything touches the device
+    assert lib.lmdec_gram_reduce(None, 20, 100, 20, None, None, None) != 0
+    assert b"multicast" in lib.lmdec_last_error()
+    assert lib.lmdec_dense_matmul(None, None, 1, 1, 1, 1, None, 0, 1, 1, None, None, None, 1, 0, None) != 0
+    assert lib.lmdec_operator_apply_reduce(None, None, 1, 1, 1, 1, 0, 9, None, 1, 4, 3, None, None, None, None, None,
+                                           None, None, None, None, None, None) != 0
 
 
 def test_library_is_sm100a_tcgen05():
@@ -36,7 +45,9 @@ def test_library_is_sm100a_tcgen05():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run(["cuobjdump", "-sass", _capi.lib_path()], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCIMMA", "STTM", "LDTM", "UBLKCP"):
+    # UTCIMMA: kind::i8 (genotypes); UTCHMMA: kind::tf32 (dense float32 operands).  (multimem.red of the fused
+    # reductions shows up as a plain REDG on a multicast address: nothing to grep for.)
+    for mnemonic in ("UTCIMMA", "UTCHMMA", "STTM", "LDTM", "UBLKCP", "USETMAXREG"):
         assert mnemonic in sass, mnemonic
 
 
